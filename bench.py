@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Msamples/s of the Complex<f32> 256-tap FIR on 64 Mi-sample
+chunks (BASELINE.json configs[1]) at N GPUs, with the HBM roofline fraction of the dominant
+kernel and the reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the FIR over one 64 Mi-sample chunk per GPU (weak scaling: each rank
+owns the next contiguous chunk of one logical stream; the only exchange is the NCCL all-gather
+of the (ntaps-1)-sample overlap region, futuresdr_b200/shard.py).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NTAPS = 256
+CHUNK = 64 * 1024 * 1024          # samples per GPU per step (BASELINE configs[1])
+BYTES_PER_SAMPLE = 16             # 8 B in + 8 B out (taps/halo amortise to 0)
+SEED = 0x5EED
+FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def _peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _taps():
+    return np.random.default_rng(7).uniform(-1, 1, NTAPS).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle port of
+# crates/futuredsp/src/fir.rs:52-91; the Rust cannot be compiled here), all host threads.
+# ------------------------------------------------------------------------------------------
+def cpu_reference(sample_items: int, reps: int = 1):
+    import oracle as orc
+    threads = orc.max_threads()
+    rng = np.random.default_rng(SEED)
+    x = (rng.standard_normal(sample_items + NTAPS - 1) + 1j * rng.standard_normal(sample_items + NTAPS - 1)
+         ).astype(np.complex64)
+    taps = _taps()
+    out = np.empty(sample_items, np.complex64)
+    best = {}
+    for fast in (False, True):
+        orc.fir_c32_f32_mt(taps, x[: 65536 + NTAPS - 1], threads, fast=fast)     # warm
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            orc.fir_c32_f32_mt(taps, x, threads, fast=fast, out=out)
+            ts.append(time.perf_counter() - t0)
+        best["nightly_reassoc" if fast else "stable_strict"] = min(ts)
+    variant = min(best, key=best.get)
+    return {"seconds": best[variant], "variant": variant, "threads": threads, "all": best,
+            "msps": sample_items / best[variant] / 1e6}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the same workload: 256-tap c32 FIR on white noise
+    n = 8 * 1024 * 1024
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference(n, reps=1)
+        last = r
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    sec = statistics.mean(times)
+    v = n / sec / 1e6
+    line = {
+        "impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic white noise",
+        "config": {"workload": "c32 256-tap FIR (BASELINE configs[1]), CPU sample of 8 Mi samples/step",
+                   "ntaps": NTAPS, "sample_items": n},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": last["threads"], "kind": "port",
+                         "sample": f"{n} samples/step, oracle port of futuredsp fir.rs:52-91 ({last['variant']}), "
+                                   f"{last['threads']} OpenMP threads over contiguous shards"},
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import futuresdr_b200 as fb
+    from futuresdr_b200.shard import ShardedFir
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    taps = _taps()
+    algo = {"auto": fb.ALGO_AUTO, "direct": fb.ALGO_DIRECT, "tensor": fb.ALGO_TENSOR}[args.algo]
+    sh = ShardedFir(taps, CHUNK, np.complex64, device=dev, algo=algo)
+    ctx = sh._filter.ctx
+    # synthetic white noise generated on the device (Philox), per-rank subsequence
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    torch.view_as_real(sh.chunk).normal_(generator=g)
+    out = torch.empty(CHUNK, dtype=torch.complex64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`): inputs already in HBM
+    for _ in range(args.warmup):
+        sh.step(out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev[0].record()
+    produced = 0
+    for i in range(args.steps):
+        # the FIR kernel alone (for the roofline): events on the launching stream around compute
+        orig = sh.compute
+
+        def timed(src, o, _i=i, _f=orig):
+            kev[_i][0].record()
+            r = _f(src, o)
+            kev[_i][1].record()
+            return r
+        sh.compute = timed
+        c, p, st = sh.step(out)
+        sh.compute = orig
+        produced += p
+        ev[i + 1].record()
+    barrier()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = [a.elapsed_time(b) for a, b in kev]
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = (CHUNK * world * args.steps) / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C-ABI host-slice call (`e2e`): pinned host in/out, H2D + D2H timed
+    fir = sh._filter
+    n_e2e = CHUNK
+    h_in = torch.empty(n_e2e + NTAPS - 1, dtype=torch.complex64).pin_memory()
+    torch.view_as_real(h_in).normal_(generator=torch.Generator().manual_seed(SEED + 100 + rank))
+    h_out = torch.empty(n_e2e, dtype=torch.complex64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        fir.filter(h_in, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        c, p, st = fir.filter(h_in, h_out)          # returns when h_out is filled
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = (n_e2e * world * e2e_steps) / float(te.item()) / 1e6
+    # parity spot check of the e2e output against the device path is done in tests/; here we
+    # only make sure the result was produced
+    assert p == n_e2e
+
+    if rank == 0:
+        peak, peak_src = _peak_hbm()
+        k_ms = statistics.mean(kern_ms)
+        achieved = BYTES_PER_SAMPLE * CHUNK / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_fir.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get({1: "direct", 2: "tensor"}.get(fir.algo, ""), None)
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            r = cpu_reference(4 * 1024 * 1024, reps=3)
+            cpu = {"value": r["msps"], "unit": "Msamples/s", "cores": r["threads"], "kind": "port",
+                   "sample": f"4 Mi samples x3 (best), same taps/noise family; oracle port of futuredsp "
+                             f"fir.rs:52-91, variant {r['variant']} (strict {4*1024*1024/r['all']['stable_strict']/1e6:.1f} / "
+                             f"reassoc {4*1024*1024/r['all']['nightly_reassoc']/1e6:.1f} Msamples/s)"}
+        line = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic white noise (device Philox, per-rank subsequence)",
+            "config": {"workload": "single-B200 Complex<f32> 256-tap FIR on 64 Mi-sample chunks via device-resident ring (BASELINE configs[1])",
+                       "ntaps": NTAPS, "chunk_items": CHUNK, "algo": {1: "direct", 2: "tensor"}.get(fir.algo),
+                       "l2": "inputs larger than L2 (512 MiB in + 512 MiB out per step)",
+                       "sharding": "contiguous time ranges, NCCL all-gather of the 255-sample overlap" if world > 1 else "none"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * CHUNK},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": (n_e2e + NTAPS - 1) * 8,
+                    "d2h_bytes_per_step": n_e2e * 8, "steps": e2e_steps,
+                    "api": "FirFilter.filter(host_in, host_out) -> b2s_fir_filter_host (pinned host, chunked H2D/kernel/D2H pipeline)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "direct", "tensor"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

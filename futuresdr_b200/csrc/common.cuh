@@ -1,0 +1,68 @@
+// common.cuh -- context object, error plumbing and small device helpers shared by all
+// translation units of libb200sdr.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b200sdr.h"
+
+struct b2s_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    // side streams + events for the host-slice pipeline (b2s_fir_filter_host)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::atomic<uint64_t> launches{0};
+    std::string err;
+    // workspace for *_host calls (grown on demand, freed with the context)
+    void *ws_dev = nullptr;
+    size_t ws_bytes = 0;
+};
+
+extern thread_local std::string g_b2s_last_error;
+
+int32_t b2s_fail(b2s_ctx *ctx, int32_t code, const char *fmt, ...);
+
+#define B2S_CUDA(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return b2s_fail((ctx), B2S_ECUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                     \
+    } while (0)
+
+#define B2S_CHECK_LAUNCH(ctx)                                                                 \
+    do {                                                                                      \
+        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                              \
+        B2S_CUDA((ctx), cudaGetLastError());                                                  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static inline size_t sat_sub(size_t a, size_t b) { return a > b ? a - b : 0; }
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+static inline size_t round_up(size_t a, size_t b) { return ceil_div(a, b) * b; }
+
+static inline size_t kind_in_bytes(b2s_kind k) { return k == B2S_F32_F32 ? 4 : 8; }
+static inline size_t kind_tap_floats(b2s_kind k) { return k == B2S_C32_C32 ? 2 : 1; }

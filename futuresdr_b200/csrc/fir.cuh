@@ -1,0 +1,32 @@
+// fir.cuh -- FIR plan object shared by the ABI layer and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+struct b2s_fir {
+    b2s_ctx *ctx = nullptr;
+    b2s_kind kind = B2S_C32_F32;
+    size_t ntaps = 0, decim = 1;
+    std::vector<float> taps_host;   // reference order, kind_tap_floats(kind) floats per tap
+    b2s_algo algo_req = B2S_ALGO_AUTO, algo = B2S_ALGO_DIRECT;
+
+    // ---- direct form (fir_direct.cu): per-phase, time-reversed, zero-padded taps in HBM.
+    // G[q][u] = g[D*u + q - (D-1)], g[t] = taps[N-1-t]   (see DESIGN.md "direct FIR")
+    float *d_ptaps = nullptr;
+    int U = 0, Upad = 0;
+
+    // ---- tensor-core form (fir_tc.cu): split-bf16 Toeplitz blocks, built lazily
+    void *d_toeplitz = nullptr;
+    int tc_kblocks = 0;
+    bool tc_ready = false;
+};
+
+// fir_direct.cu
+int32_t fir_direct_prepare(b2s_fir *f);
+int32_t fir_direct_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                          cudaStream_t stream);
+// fir_tc.cu
+bool    fir_tc_supported(const b2s_fir *f);
+int32_t fir_tc_prepare(b2s_fir *f);
+int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                      cudaStream_t stream);
+void    fir_tc_release(b2s_fir *f);

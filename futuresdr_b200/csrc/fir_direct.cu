@@ -1,0 +1,280 @@
+// fir_direct.cu -- CUDA-core direct-form FIR / decimating FIR for sm_100a.
+//
+// Computes the reference's   o[k] = sum_t i[D-1 + k*D + t] * taps[N-1-t]
+// (crates/futuredsp/src/fir.rs:77-88 for D == 1, decimating_fir.rs:80-92 for D > 1) for the
+// three sample/tap kinds futuredsp implements (fir.rs:206-276).
+//
+// Design (see DESIGN.md "direct FIR"):
+//  * a CTA produces TK = THREADS*R consecutive outputs; it stages the D*(TK+Upad) input items
+//    it needs in shared memory, DE-INTERLEAVED into D phase rows  x_q[m] = x[D*m + q], so the
+//    decimator becomes D ordinary (stride-1) FIRs  o[k] = sum_q sum_u x_q[k+u] * G_q[u]
+//    and the inner loop is identical for every D;
+//  * each thread owns R consecutive outputs and slides an R+R-1 item register window over
+//    its phase row: one 16-byte-vector segment load (R items) + R taps feed R*R MACs, so the
+//    kernel is FMA-issue bound, not LDS bound;
+//  * shared memory is XOR-swizzled at 16-byte granularity (chunk ^= (chunk>>3)&7) so the
+//    R-item-strided segment loads of a quarter-warp hit 8 distinct bank groups;
+//  * results are transposed through shared memory so global stores are fully coalesced
+//    16-byte vectors; loads are float4-vectorised when D == 1.
+// Accumulation is FP32 FMA; the summation order differs from the reference's strict
+// left-to-right order (it is tap-order within a thread, but fused): parity is to 1e-5 relative
+// (tests/test_gpu_fir.py).
+#include "fir.cuh"
+
+namespace {
+
+__device__ __forceinline__ int swz(int chunk) { return chunk ^ ((chunk >> 3) & 7); }
+
+__device__ __forceinline__ void mac(float &a, float x, float t) { a = fmaf(x, t, a); }
+__device__ __forceinline__ void mac(float2 &a, float2 x, float t) {
+    a.x = fmaf(x.x, t, a.x);
+    a.y = fmaf(x.y, t, a.y);
+}
+// Complex tap: accum + sample*tap, re = xr*tr - xi*ti, im = xr*ti + xi*tr (fir.rs:257-276)
+__device__ __forceinline__ void mac(float2 &a, float2 x, float2 t) {
+    a.x = fmaf(x.x, t.x, a.x);
+    a.x = fmaf(-x.y, t.y, a.x);
+    a.y = fmaf(x.x, t.y, a.y);
+    a.y = fmaf(x.y, t.x, a.y);
+}
+
+template <typename S> __device__ __forceinline__ S zero_of();
+template <> __device__ __forceinline__ float zero_of<float>() { return 0.0f; }
+template <> __device__ __forceinline__ float2 zero_of<float2>() { return make_float2(0.f, 0.f); }
+
+template <typename S, int R>
+__device__ __forceinline__ void load_segment(S (&dst)[R], const unsigned char *row, int seg) {
+    constexpr int EPC = 16 / sizeof(S);   // items per 16-byte chunk
+    constexpr int CPS = R / EPC;          // chunks per R-item segment
+#pragma unroll
+    for (int j = 0; j < CPS; j++) {
+        const int chunk = seg * CPS + j;
+        const float4 v = *reinterpret_cast<const float4 *>(row + swz(chunk) * 16);
+        if constexpr (sizeof(S) == 8) {
+            dst[2 * j] = *reinterpret_cast<const S *>(&v.x);
+            dst[2 * j + 1] = *reinterpret_cast<const S *>(&v.z);
+        } else {
+            dst[4 * j] = *reinterpret_cast<const S *>(&v.x);
+            dst[4 * j + 1] = *reinterpret_cast<const S *>(&v.y);
+            dst[4 * j + 2] = *reinterpret_cast<const S *>(&v.z);
+            dst[4 * j + 3] = *reinterpret_cast<const S *>(&v.w);
+        }
+    }
+}
+
+// S: sample type (float | float2), T: tap type (float | float2)
+template <typename S, typename T, int R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+fir_direct_kernel(const S *__restrict__ in, S *__restrict__ out, const T *__restrict__ ptaps,
+                  int D, int Upad, int pitch /*items per phase row, multiple of 8 chunks*/,
+                  long long n_in, long long n_out, int vec_ok) {
+    constexpr int EPC = 16 / sizeof(S);
+    constexpr int TK = THREADS * R;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const long long k0 = (long long)blockIdx.x * TK;
+    const int W = TK + Upad;                       // items needed per phase row
+    unsigned char *xs = smem;                      // [D][pitch] items, swizzled per row
+    T *gs = reinterpret_cast<T *>(smem + (size_t)D * pitch * sizeof(S));   // [D][Upad]
+
+    // ---- stage taps
+    for (int j = tid; j < D * Upad; j += THREADS) gs[j] = ptaps[j];
+
+    // ---- stage inputs, de-interleaving phases
+    const long long s0 = k0 * D;                   // first input item of this tile
+    if (D == 1 && vec_ok) {
+        const int nchunks = (W + EPC - 1) / EPC;
+        for (int c = tid; c < nchunks; c += THREADS) {
+            const long long s = s0 + (long long)c * EPC;
+            float4 v;
+            if (s + EPC <= n_in) {
+                v = __ldg(reinterpret_cast<const float4 *>(in + s));
+            } else {
+                S tmp[EPC];
+#pragma unroll
+                for (int e = 0; e < EPC; e++) tmp[e] = (s + e < n_in) ? in[s + e] : zero_of<S>();
+                v = *reinterpret_cast<float4 *>(tmp);
+            }
+            *reinterpret_cast<float4 *>(xs + swz(c) * 16) = v;
+        }
+    } else {
+        // item j of the tile -> phase q = j % D, row index m = j / D (s0 is a multiple of D)
+        const int total = D * W;
+        int q = tid % D, m = tid / D;
+        const int dq = THREADS % D, dm = THREADS / D;
+        for (int j = tid; j < total; j += THREADS) {
+            const long long s = s0 + j;
+            const S v = (s < n_in) ? in[s] : zero_of<S>();
+            const int chunk = m / EPC, e = m % EPC;
+            *reinterpret_cast<S *>(xs + ((size_t)q * pitch + swz(chunk) * EPC + e) * sizeof(S)) = v;
+            q += dq; m += dm;
+            if (q >= D) { q -= D; m += 1; }
+        }
+    }
+    __syncthreads();
+
+    // ---- R outputs per thread, sliding register window
+    S acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = zero_of<S>();
+
+    const int nchunk_taps = Upad / R;
+    for (int q = 0; q < D; q++) {
+        const unsigned char *row = xs + (size_t)q * pitch * sizeof(S);
+        const T *g = gs + q * Upad;
+        S win[2 * R];
+        {
+            S first[R];
+            load_segment<S, R>(first, row, tid);
+#pragma unroll
+            for (int r = 0; r < R; r++) win[r] = first[r];
+        }
+        for (int c = 0; c < nchunk_taps; c++) {
+            S nxt[R];
+            load_segment<S, R>(nxt, row, tid + c + 1);
+#pragma unroll
+            for (int r = 0; r < R; r++) win[R + r] = nxt[r];
+            T tp[R];
+            {
+                // taps are warp-uniform: 16-byte broadcast loads (g + c*R is 32-byte aligned)
+                constexpr int NV = R * sizeof(T) / 16;
+                const float4 *gv = reinterpret_cast<const float4 *>(g + c * R);
+#pragma unroll
+                for (int v = 0; v < NV; v++) reinterpret_cast<float4 *>(tp)[v] = gv[v];
+            }
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) mac(acc[r], win[r + j], tp[j]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) win[r] = win[R + r];
+        }
+    }
+    __syncthreads();                                // everyone is done reading xs
+
+    // ---- transpose through smem, coalesced vector stores
+    {
+        constexpr int CPS = R / EPC;
+#pragma unroll
+        for (int j = 0; j < CPS; j++) {
+            const int chunk = tid * CPS + j;
+            float4 v;
+            if constexpr (sizeof(S) == 8) {
+                v = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
+            } else {
+                v = make_float4(*reinterpret_cast<float *>(&acc[4 * j]),
+                                *reinterpret_cast<float *>(&acc[4 * j + 1]),
+                                *reinterpret_cast<float *>(&acc[4 * j + 2]),
+                                *reinterpret_cast<float *>(&acc[4 * j + 3]));
+            }
+            *reinterpret_cast<float4 *>(xs + swz(chunk) * 16) = v;
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int NCH = TK / EPC;
+        for (int c = tid; c < NCH; c += THREADS) {
+            const long long k = k0 + (long long)c * EPC;
+            if (k >= n_out) break;
+            const float4 v = *reinterpret_cast<const float4 *>(xs + swz(c) * 16);
+            if (vec_ok && k + EPC <= n_out) {
+                *reinterpret_cast<float4 *>(out + k) = v;
+            } else {
+                const S *p = reinterpret_cast<const S *>(&v);
+#pragma unroll
+                for (int e = 0; e < EPC; e++)
+                    if (k + e < n_out) out[k + e] = p[e];
+            }
+        }
+    }
+}
+
+// Fallback for exotic shapes (very large decimation): one thread per output, straight from
+// global memory (L1/L2 cached), reference tap order.
+template <typename S, typename T>
+__global__ void fir_naive_kernel(const S *__restrict__ in, S *__restrict__ out,
+                                 const T *__restrict__ rtaps /* g[t] = taps[N-1-t] */, int N, int D,
+                                 long long n_out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_out) return;
+    const S *x = in + (long long)D * k + (D - 1);
+    S acc = zero_of<S>();
+    for (int t = 0; t < N; t++) mac(acc, x[t], rtaps[t]);
+    out[k] = acc;
+}
+
+constexpr int kThreads = 128;
+constexpr int kR = 8;
+constexpr size_t kSmemBudget = 160 * 1024;
+
+template <typename S, typename T>
+int32_t launch_typed(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                     cudaStream_t stream) {
+    b2s_ctx *ctx = f->ctx;
+    constexpr int EPC = 16 / sizeof(S);
+    constexpr int TK = kThreads * kR;
+    const int D = (int)f->decim;
+    const int W = TK + f->Upad;
+    const int pitch = (int)round_up((size_t)W, 8 * EPC);
+    const size_t smem = (size_t)D * pitch * sizeof(S) + (size_t)D * f->Upad * sizeof(T);
+    if (smem > kSmemBudget) {
+        // taps for the naive kernel: phase table row-major does not apply; use d_ptaps tail
+        const T *rt = reinterpret_cast<const T *>(f->d_ptaps) + (size_t)D * f->Upad;
+        const int th = 256;
+        fir_naive_kernel<S, T><<<(unsigned)ceil_div(n_out, th), th, 0, stream>>>(
+            (const S *)d_in, (S *)d_out, rt, (int)f->ntaps, D, (long long)n_out);
+        B2S_CHECK_LAUNCH(ctx);
+        return B2S_OK;
+    }
+    auto kern = fir_direct_kernel<S, T, kR, kThreads>;
+    static thread_local bool attr_set = false;   // per template instantiation + thread
+    if (!attr_set) {
+        B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kSmemBudget));
+        attr_set = true;
+    }
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    const unsigned grid = (unsigned)ceil_div(n_out, (size_t)TK);
+    kern<<<grid, kThreads, smem, stream>>>((const S *)d_in, (S *)d_out, (const T *)f->d_ptaps, D,
+                                           f->Upad, pitch, (long long)n_in, (long long)n_out, vec_ok);
+    B2S_CHECK_LAUNCH(ctx);
+    return B2S_OK;
+}
+
+}  // namespace
+
+// Build G[q][u] (phase-major, reversed, zero padded to a multiple of R) followed by the plain
+// reversed taps g[t] (used by the naive fallback).
+int32_t fir_direct_prepare(b2s_fir *f) {
+    b2s_ctx *ctx = f->ctx;
+    const size_t N = f->ntaps, D = f->decim, tf = kind_tap_floats(f->kind);
+    f->U = (int)((N + D - 2) / D + 1);
+    f->Upad = (int)round_up((size_t)f->U, kR);
+    std::vector<float> h((D * f->Upad + N) * tf, 0.0f);
+    for (size_t q = 0; q < D; q++)
+        for (size_t u = 0; u < (size_t)f->U; u++) {
+            const long long idx = (long long)(D * u + q) - (long long)(D - 1);
+            if (idx < 0 || idx >= (long long)N) continue;
+            for (size_t c = 0; c < tf; c++)
+                h[(q * f->Upad + u) * tf + c] = f->taps_host[(N - 1 - idx) * tf + c];
+        }
+    for (size_t t = 0; t < N; t++)
+        for (size_t c = 0; c < tf; c++) h[(D * f->Upad + t) * tf + c] = f->taps_host[(N - 1 - t) * tf + c];
+    B2S_CUDA(ctx, cudaMalloc((void **)&f->d_ptaps, h.size() * sizeof(float)));
+    B2S_CUDA(ctx, cudaMemcpyAsync(f->d_ptaps, h.data(), h.size() * sizeof(float),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h goes out of scope
+    return B2S_OK;
+}
+
+int32_t fir_direct_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                          cudaStream_t stream) {
+    if (n_out == 0) return B2S_OK;
+    switch (f->kind) {
+        case B2S_F32_F32: return launch_typed<float, float>(f, d_in, n_in, d_out, n_out, stream);
+        case B2S_C32_F32: return launch_typed<float2, float>(f, d_in, n_in, d_out, n_out, stream);
+        case B2S_C32_C32: return launch_typed<float2, float2>(f, d_in, n_in, d_out, n_out, stream);
+    }
+    return b2s_fail(f->ctx, B2S_EINVAL, "bad kind");
+}

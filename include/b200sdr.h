@@ -1,0 +1,204 @@
+/*
+ * b200sdr.h -- C ABI of the B200-native streaming-DSP backend for FutureSDR's
+ * FIR / decimator / resampler / FFT / Apply / PfbArbResampler hot path.
+ *
+ * The reference (FutureSDR, Rust) has no FFI for this path: its boundary is a set of Rust
+ * traits.  Every entry point below names the reference interface it replaces (file:line is
+ * relative to the FutureSDR tree).  INTEGRATION.md shows the Rust `extern "C"` block and the
+ * `impl futuredsp::Filter` / `impl Kernel` shims a maintainer would add on top of this header.
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = B2S_OK, <0 = B2S_E*; b2s_last_error() gives text.
+ *     No exception crosses the boundary, no torch/CUDA type appears in a signature
+ *     (a CUDA stream is passed as void*).
+ *   - handles are opaque; a handle is used by one caller at a time (thread-compatible),
+ *     different handles may be used concurrently.
+ *   - Complex<f32> is interleaved {re, im} (num_complex is repr(C)); item counts are in
+ *     ITEMS (samples), never bytes, exactly like the Rust slices they replace.
+ *   - *_exec calls take DEVICE pointers, are asynchronous and ordered on the context's
+ *     stream; the (consumed, produced, status) triple is a pure function of the sizes and is
+ *     returned immediately.  *_host calls take HOST pointers and return when the output is
+ *     in host memory (they are the literal drop-in for `Filter::filter(&[In], &mut [Out])`).
+ */
+#ifndef B200SDR_H
+#define B200SDR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define B2S_OK            0
+#define B2S_EINVAL       (-1) /* bad argument (the reference would panic/assert)            */
+#define B2S_ECUDA        (-2) /* CUDA runtime error; sticky, see b2s_last_error             */
+#define B2S_ENOMEM       (-3)
+#define B2S_EAGAIN       (-4) /* ring: no buffer available right now (not an error)         */
+#define B2S_EUNSUPPORTED (-5) /* combination the reference supports but this build does not */
+#define B2S_ESTATE       (-6) /* slot/ring used out of order                                */
+
+/* futuredsp::ComputationStatus  (crates/futuredsp/src/lib.rs:33-45) */
+#define B2S_INSUFFICIENT_INPUT  0
+#define B2S_INSUFFICIENT_OUTPUT 1
+#define B2S_BOTH_SUFFICIENT     2
+
+/* sample x tap kinds = the Filter impls that exist in futuredsp
+ * (fir.rs:206-276, decimating_fir.rs:99-300, polyphase_resampling_fir.rs:126-167) */
+typedef enum {
+    B2S_F32_F32 = 0, /* f32 samples, f32 taps                 */
+    B2S_C32_F32 = 1, /* Complex<f32> samples, f32 taps        */
+    B2S_C32_C32 = 2  /* Complex<f32> samples, Complex<f32> taps */
+} b2s_kind;
+
+/* FIR algorithm selection (no reference equivalent; AUTO picks by tap count / kind) */
+typedef enum {
+    B2S_ALGO_AUTO   = 0,
+    B2S_ALGO_DIRECT = 1, /* CUDA-core register-blocked direct form (any kind, any decimation) */
+    B2S_ALGO_TENSOR = 2  /* tcgen05 block-Toeplitz GEMM, split-bf16 (real taps, decim == 1)   */
+} b2s_algo;
+
+typedef struct b2s_ctx    b2s_ctx;
+typedef struct b2s_fir    b2s_fir;
+typedef struct b2s_resamp b2s_resamp;
+typedef struct b2s_pfbarb b2s_pfbarb;
+typedef struct b2s_fft    b2s_fft;
+typedef struct b2s_apply  b2s_apply;
+typedef struct b2s_ring   b2s_ring;
+typedef struct b2s_slot   b2s_slot;
+
+/* ---- context (replaces runtime::buffer::vulkan::Instance, buffer/vulkan/mod.rs:45-153) -- */
+int32_t     b2s_version(void);
+/* stream == NULL: the context creates its own non-blocking stream.  Otherwise `stream` is a
+ * cudaStream_t owned by the caller (e.g. torch's current stream) and all work is ordered on it. */
+int32_t     b2s_ctx_create(int device, void *stream, b2s_ctx **out);
+void        b2s_ctx_destroy(b2s_ctx *ctx);
+const char *b2s_last_error(const b2s_ctx *ctx); /* ctx may be NULL: last global error       */
+int32_t     b2s_ctx_sync(b2s_ctx *ctx);         /* ≙ awaiting the fence, blocks/vulkan.rs:157-162 */
+void       *b2s_ctx_stream(b2s_ctx *ctx);
+int32_t     b2s_ctx_sm_count(b2s_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t    b2s_ctx_launch_count(const b2s_ctx *ctx);
+
+/* device / pinned-host memory (≙ Instance::create_buffer, buffer/vulkan/mod.rs:132) */
+int32_t b2s_malloc(b2s_ctx *ctx, size_t bytes, void **dptr);
+int32_t b2s_free(b2s_ctx *ctx, void *dptr);
+int32_t b2s_host_alloc(b2s_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int32_t b2s_host_free(b2s_ctx *ctx, void *hptr);
+int32_t b2s_memcpy_h2d(b2s_ctx *ctx, void *dptr, const void *hptr, size_t bytes); /* async */
+int32_t b2s_memcpy_d2h(b2s_ctx *ctx, void *hptr, const void *dptr, size_t bytes); /* async */
+
+/* ---- FIR plans (≙ FirFilter::new fir.rs:39-46, DecimatingFirFilter::new decimating_fir.rs:41-49)
+ * taps: ntaps items of f32 (or interleaved Complex<f32> for B2S_C32_C32), in the SAME order the
+ * reference takes them (the filter applies them reversed, fir.rs:84); copied at creation.
+ * decim == 1 gives FirFilter, decim > 1 DecimatingFirFilter. */
+int32_t b2s_fir_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntaps, size_t decim,
+                     b2s_fir **out);
+int32_t b2s_fir_plan_f32_f32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t decim, b2s_fir **out);
+int32_t b2s_fir_plan_c32_f32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t decim, b2s_fir **out);
+int32_t b2s_fir_plan_c32_c32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t decim, b2s_fir **out);
+void    b2s_fir_destroy(b2s_fir *f);
+size_t  b2s_fir_length(const b2s_fir *f);           /* ≙ Filter::length, lib.rs:65-67 */
+int32_t b2s_fir_set_algo(b2s_fir *f, b2s_algo algo);
+int32_t b2s_fir_get_algo(const b2s_fir *f);         /* the algorithm AUTO resolved to */
+
+/* ≙ Filter::filter (lib.rs:58-64; cores fir.rs:52-91, decimating_fir.rs:53-95): device slices.
+ * Elements of d_out beyond *produced are left unspecified, as in the reference. */
+int32_t b2s_fir_exec(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                     size_t *consumed, size_t *produced, int32_t *status);
+/* Same contract with host slices (pageable or pinned): chunked H2D -> kernel -> D2H pipeline
+ * through an internal device ring; returns after the last D2H completed. */
+int32_t b2s_fir_filter_host(b2s_fir *f, const void *h_in, size_t n_in, void *h_out, size_t n_out_cap,
+                            size_t *consumed, size_t *produced, int32_t *status);
+
+/* ---- rational polyphase resampler (≙ PolyphaseResamplingFir, polyphase_resampling_fir.rs:42-124)
+ * kinds B2S_F32_F32 and B2S_C32_F32 (the only impls, :126-167); ntaps % interp == 0 (:56). */
+int32_t b2s_resamp_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntaps, size_t interp,
+                        size_t decim, b2s_resamp **out);
+void    b2s_resamp_destroy(b2s_resamp *r);
+size_t  b2s_resamp_length(const b2s_resamp *r);
+int32_t b2s_resamp_exec(b2s_resamp *r, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                        size_t *consumed, size_t *produced, int32_t *status);
+
+/* ---- PfbArbResampler (≙ src/blocks/pfb/arb_resampler.rs:90-231; Complex<f32> only).
+ * Stateful like the block: one exec == one Kernel::work call (window fill first, :199-215). */
+int32_t b2s_pfbarb_plan_c32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t num_filters,
+                            float rate, b2s_pfbarb **out);
+void    b2s_pfbarb_destroy(b2s_pfbarb *p);
+int32_t b2s_pfbarb_reset(b2s_pfbarb *p);
+int32_t b2s_pfbarb_exec(b2s_pfbarb *p, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                        size_t *consumed, size_t *produced, int32_t *call_again);
+
+/* ---- FFT (≙ Fft::with_options, src/blocks/fft.rs:66-121, and Fft::work :160-221) ---------
+ * inverse: FftDirection; fft_shift, normalize as in with_options (has_normalize = Option::is_some).
+ * One exec processes m = floor(min(n_in, n_out_cap)/n)*n items (no 32-FFT cap: the cap only
+ * splits work across calls, fft.rs:171). */
+int32_t b2s_fft_plan_c32(b2s_ctx *ctx, size_t n, int32_t inverse, int32_t fft_shift,
+                         int32_t has_normalize, float normalize, b2s_fft **out);
+void    b2s_fft_destroy(b2s_fft *f);
+size_t  b2s_fft_length(const b2s_fft *f);
+int32_t b2s_fft_exec(b2s_fft *f, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                     size_t *consumed, size_t *produced);
+
+/* ---- Apply (≙ src/blocks/apply.rs:100-131).  The reference takes an arbitrary Rust closure;
+ * the device version is a closed catalogue of the closures used on the path. */
+typedef enum {
+    B2S_OP_SCALE_F32     = 0, /* f32 -> f32: x * param          (tests/vulkan.rs:16-27, blocks/wgpu.rs:22-32) */
+    B2S_OP_SCALE_C32     = 1, /* c32 -> c32: x * param                                                       */
+    B2S_OP_QUAD_DEMOD    = 2, /* c32 -> f32: arg(x[n] * conj(x[n-1])), stateful (examples/fm-receiver/src/main.rs:99-104) */
+    B2S_OP_NORM_SQR      = 3, /* c32 -> f32: re^2 + im^2        (examples/spectrum/src/bin/cpu.rs)            */
+    B2S_OP_QUAD_DEMOD_C32 = 4, /* c32 -> c32 {re: phase, im: 0}: demod packed for PfbArbResampler */
+    B2S_OP_EXP_F32       = 5, /* f32 -> f32: exp(x)            (examples/vulkan/src/main.rs:17-29)            */
+    B2S_OP_MAG_C32       = 6, /* c32 -> f32: sqrt(re^2 + im^2)                                               */
+    B2S_OP_LOG10_F32     = 7  /* f32 -> f32: param * log10(x)   (spectrum dB stage)                           */
+} b2s_op;
+int32_t b2s_apply_create(b2s_ctx *ctx, b2s_op op, float param, b2s_apply **out);
+void    b2s_apply_destroy(b2s_apply *a);
+int32_t b2s_apply_reset(b2s_apply *a); /* closure state back to its initial value */
+/* m = min(n_in, n_out_cap) items are processed (apply.rs:109) */
+int32_t b2s_apply_exec(b2s_apply *a, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                       size_t *consumed, size_t *produced);
+
+/* ---- device-resident buffer ring (≙ buffer/vulkan/{h2d,d2h}.rs + circuit.rs + slab.rs history)
+ * n_slots buffers of `halo_items + chunk_items` items each stay in HBM; ownership of a slot
+ * moves source-edge -> GPU block(s) -> sink-edge -> back (circuit), exactly like
+ * vulkan::Buffer (h2d.rs:161-232, d2h.rs:66-74, :270-299).  Each slot has pinned host staging
+ * for the H2D / D2H edges when with_host_staging != 0. */
+int32_t b2s_ring_create(b2s_ctx *ctx, size_t item_bytes, size_t chunk_items, size_t halo_items,
+                        int32_t n_slots, int32_t with_host_staging, b2s_ring **out);
+void    b2s_ring_destroy(b2s_ring *r);
+/* ≙ H2DWriter: pop an empty buffer from `inbound` (h2d.rs:178-197); B2S_EAGAIN if none */
+int32_t b2s_ring_acquire_empty(b2s_ring *r, b2s_slot **slot);
+/* ≙ H2DWriter::produce -> outbound.push + notify (h2d.rs:199-232).  from_host != 0 first
+ * enqueues the pinned->device copy of valid_items. */
+int32_t b2s_ring_submit_full(b2s_ring *r, b2s_slot *slot, size_t valid_items, int32_t from_host);
+/* ≙ H2DReader::buffers() / D2HReader (h2d.rs:276, d2h.rs:247-268); B2S_EAGAIN if none */
+int32_t b2s_ring_acquire_full(b2s_ring *r, b2s_slot **slot, size_t *valid_items);
+/* ≙ D2HReader::consume -> buffer back to the circuit start (d2h.rs:270-299) */
+int32_t b2s_ring_release(b2s_ring *r, b2s_slot *slot);
+/* slab.rs:370-398: copy the unconsumed tail (`tail_items` <= halo_items) of `from` in front of
+ * `to`'s data so the next block sees contiguous history. */
+int32_t b2s_ring_carry_halo(b2s_ring *r, const b2s_slot *from, size_t from_valid, size_t tail_items,
+                            b2s_slot *to);
+void   *b2s_slot_device_ptr(const b2s_slot *slot); /* first data item; halo lives just below   */
+void   *b2s_slot_host_ptr(const b2s_slot *slot);   /* pinned staging (NULL without staging)    */
+size_t  b2s_slot_halo_valid(const b2s_slot *slot); /* items of history currently in front      */
+int32_t b2s_slot_fetch_to_host(b2s_slot *slot, size_t items); /* async D2H into staging + event */
+int32_t b2s_slot_wait(b2s_slot *slot);             /* host wait on the slot's event            */
+size_t  b2s_ring_free_slots(const b2s_ring *r);
+size_t  b2s_ring_full_slots(const b2s_ring *r);
+
+/* ---- tap design, host side, f64 then cast (≙ futuredsp::firdes::kaiser, firdes/basic.rs:310-459)
+ * Return the tap count; write taps only if cap is large enough (call with taps=NULL to size). */
+size_t b2s_firdes_kaiser_lowpass(double cutoff, double transition_bw, double max_ripple,
+                                 float *taps, size_t cap);
+size_t b2s_firdes_kaiser_multirate(size_t interp, size_t decim, size_t half_polyphase_len,
+                                   double max_ripple, float *taps, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SDR_H */
