@@ -25,7 +25,8 @@ _szp, _i32p, _vpp, _f32p = C.POINTER(C.c_size_t), C.POINTER(C.c_int32), C.POINTE
 # name -> (restype, argtypes): one entry per function declared in include/b200sdr.h
 SIGNATURES = {
     "b2s_version": (_i32, []),
-    "b2s_ctx_create": (_i32, [C.c_int, _vp, _vpp]),
+    "b2s_ctx_create": (_i32, [C.c_int, _vpp]),
+    "b2s_ctx_create_on_stream": (_i32, [C.c_int, _vp, _vpp]),
     "b2s_ctx_destroy": (None, [_vp]),
     "b2s_last_error": (C.c_char_p, [_vp]),
     "b2s_ctx_sync": (_i32, [_vp]),

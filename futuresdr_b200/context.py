@@ -24,7 +24,11 @@ class Context:
                 raise RuntimeError("futuresdr_b200 needs a CUDA device (no CPU fallback)")
             stream = torch.cuda.current_stream(self.device).cuda_stream
         h = C.c_void_p()
-        check(lib.b2s_ctx_create(self.device, C.c_void_p(stream or 0), C.byref(h)))
+        if own_stream:
+            check(lib.b2s_ctx_create(self.device, C.byref(h)))
+        else:
+            # NB: torch's default stream has handle 0 (the legacy default stream) -- still "on stream"
+            check(lib.b2s_ctx_create_on_stream(self.device, C.c_void_p(stream or 0), C.byref(h)))
         self._h = h
 
     @property

@@ -21,7 +21,7 @@ extern "C" {
 
 int32_t b2s_version(void) { return B2S_VERSION; }
 
-int32_t b2s_ctx_create(int device, void *stream, b2s_ctx **out) {
+static int32_t ctx_create(int device, void *stream, bool own, b2s_ctx **out) {
     if (!out) return b2s_fail(nullptr, B2S_EINVAL, "b2s_ctx_create: out is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -44,7 +44,7 @@ int32_t b2s_ctx_create(int device, void *stream, b2s_ctx **out) {
         delete ctx;
         return rc;
     }
-    if (stream) {
+    if (!own) {
         ctx->stream = (cudaStream_t)stream;
     } else {
         B2S_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -54,6 +54,11 @@ int32_t b2s_ctx_create(int device, void *stream, b2s_ctx **out) {
     B2S_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     *out = ctx;
     return B2S_OK;
+}
+
+int32_t b2s_ctx_create(int device, b2s_ctx **out) { return ctx_create(device, nullptr, true, out); }
+int32_t b2s_ctx_create_on_stream(int device, void *stream, b2s_ctx **out) {
+    return ctx_create(device, stream, false, out);
 }
 
 void b2s_ctx_destroy(b2s_ctx *ctx) {
@@ -129,8 +134,8 @@ int32_t b2s_memcpy_d2h(b2s_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
  * ---------------------------------------------------------------------------------------- */
 static void resolve_algo(b2s_fir *f) {
     if (f->algo_req == B2S_ALGO_TENSOR && fir_tc_supported(f)) f->algo = B2S_ALGO_TENSOR;
-    else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= 48)
-        f->algo = B2S_ALGO_TENSOR;
+    else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= 48 && getenv("B2S_TC_AUTO"))
+        f->algo = B2S_ALGO_TENSOR;   // TODO(bring-up): make unconditional once the tensor path is verified
     else f->algo = B2S_ALGO_DIRECT;
 }
 

@@ -18,6 +18,7 @@ struct b2s_fir {
     void *d_toeplitz = nullptr;
     int tc_kblocks = 0;
     bool tc_ready = false;
+    int tc_flags = 0;            // bring-up switches (env B2S_TC_FLAGS)
 };
 
 // fir_direct.cu

@@ -1,9 +1,439 @@
-// fir_tc.cu -- tcgen05 block-Toeplitz FIR (placeholder until the tensor-core path lands).
+// fir_tc.cu -- tcgen05 (5th-gen tensor core) FIR for long real-tap filters on sm_100a.
+//
+// Computes the same  o[k] = sum_t i[k+t] * taps[N-1-t]  as crates/futuredsp/src/fir.rs:77-88
+// (Complex<f32> or f32 samples, f32 taps, no decimation) as a block-Toeplitz GEMM:
+//
+//      D[p][c] = sum_kappa A[p][kappa] * B[c][kappa]            (M=128, N=64, K=128*DK)
+//      A[p][kappa] = g[kappa - p]   (g[t] = taps[N-1-t], zero outside [0,N))   -- "taps, Toeplitz"
+//      B[c][kappa] = w_c[kappa]     (column c = one 128-sample block of the re- or im-stream,
+//                                    extended by the following blocks)         -- "samples"
+//      => D[p][c] = y[128*block(c) + p]
+//
+//  * A is constant: it lives in TENSOR MEMORY for the whole (persistent) kernel, written once
+//    per CTA with tcgen05.st -- the MMAs are issued in the .ts form (A from TMEM, B from smem),
+//    so the only shared-memory operand traffic is the sample tile itself.
+//  * FP32 accuracy on bf16 tensor cores: x = x_hi + x_lo, g = g_hi + g_lo (bf16 each) and
+//    x*g ~= x_hi*g_hi + x_lo*g_hi + x_hi*g_lo, three kind::f16 MMAs accumulating in FP32 in
+//    TMEM.  Dropped terms are O(2^-17) relative per product (DESIGN.md "tensor FIR numerics").
+//  * B rows are K-major, 128-byte swizzled.  K-block d of row (stream, block b) is row
+//    (stream, block b+d): a shifted view of the same tile.  Rows are stored so that the shift
+//    is a whole 8-row swizzle atom: physical atom gamma holds blocks {gamma + 8*jb}; the view
+//    for shift d starts at atom d (descriptor base + 1024*d bytes).  Atoms 8,9 duplicate the
+//    rows they alias (25 % extra conversion work, no extra HBM traffic).
+//  * warp roles: warps 0-3 producers (coalesced LDG.128 -> split to bf16 hi/lo -> swizzled
+//    st.shared), warps 4-7 epilogue (tcgen05.ld -> coalesced float2 stores; lane p of TMEM is
+//    output phase p, adjacent columns are re/im of the same block), warp 8 issues the MMAs.
+//    smem stages and the two TMEM accumulators are handed over with mbarriers.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
 #include "fir.cuh"
 
-bool fir_tc_supported(const b2s_fir *) { return false; }
-int32_t fir_tc_prepare(b2s_fir *f) { return b2s_fail(f->ctx, B2S_EUNSUPPORTED, "tensor path not built"); }
-int32_t fir_tc_launch(b2s_fir *f, const void *, size_t, void *, size_t, cudaStream_t) {
-    return b2s_fail(f->ctx, B2S_EUNSUPPORTED, "tensor path not built");
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kNumProducerThreads = 128;
+constexpr int kNumEpilogueThreads = 128;
+constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 288
+constexpr int kAtomsOut = 8;                 // N = 64 columns = 8 swizzle atoms of 8 rows
+constexpr int kMaxDK = 3;                    // K <= 384  (TMEM: K columns of taps + 128 of accumulators)
+constexpr int kSplitBytesMax = (kAtomsOut + kMaxDK - 1) * 1024 * 2;   // per split: 2 K-chunks x 10 atoms
+constexpr int kStageBytes = 2 * kSplitBytesMax;                       // hi + lo = 40 KiB
+constexpr int kSmemTC = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-void fir_tc_release(b2s_fir *) {}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16: bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// f32 pair -> packed bf16x2 {lo16 = a, hi16 = b}, round-to-nearest-even
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// split (a, b) into bf16 hi pair and bf16 lo pair:  x ~= hi + lo
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    hi = pack_bf16x2(a, b);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+    lo = pack_bf16x2(a - ah, b - bh);
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type [61,64) = 2)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major) = 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 B between 8-row atoms
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, M=128, N=64
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+    const float *in;      // samples (float2 when COMPLEX)
+    float *out;
+    const float *g;       // g[t] = taps[N-1-t], t in [0, ntaps)
+    long long n_in;       // items
+    long long n_out;      // items
+    int ntaps;
+    int DK;               // K blocks of 128
+    int num_tiles;
+    int flags;            // bit0: swap bf16 halves of the TMEM A words (bring-up switch)
+};
+
+// ---------------------------------------------------------------------------------------------
+// COMPLEX: rows are (stream ri, block b); a tile = 32 blocks x 128 complex samples, column
+//          c = 8*gamma + 2*jb + ri  <->  block b0 + gamma + 8*jb.
+// REAL   : a tile = 64 blocks x 128 samples, column c = 8*gamma + j <-> block b0 + gamma + 8*j.
+// ---------------------------------------------------------------------------------------------
+template <bool COMPLEX>
+__global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams prm) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the 128B-swizzle atoms
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char *gen_base = smem_raw + (base - raw);
+    const uint32_t bar_base = base + kStages * kStageBytes;
+    // barriers: full[kStages], empty[kStages], tfull[2], tempty[2], then tmem address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    volatile uint32_t *tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t *>(gen_base + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int DK = prm.DK, K = 128 * DK;
+    const int atoms = kAtomsOut + DK - 1;            // physical 8-row atoms per K-chunk
+    const int chunk_bytes = atoms * 1024;            // one K-chunk (64 elements) of all rows
+    const int split_bytes = 2 * chunk_bytes;
+    constexpr int NSEQ = COMPLEX ? 4 : 8;            // interleaved block sub-sequences
+    constexpr int TILE_BLOCKS = 8 * NSEQ;            // 32 / 64 blocks of 128 samples
+    constexpr long long TILE_ITEMS = (long long)TILE_BLOCKS * 128;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_gen;
+    const uint32_t tmem_acc = tmem + (uint32_t)K;    // columns [K, K+128): two 64-column accumulators
+
+    // ---- one-time: Toeplitz taps into TMEM (epilogue warps own lanes 32*(warp%4)...)
+    if (warp >= 4 && warp < 8) {
+        const int q = warp - 4, p = 32 * q + lane;   // TMEM lane = output phase p
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+        for (int c0 = 0; c0 < K / 2; c0 += 8) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int k0 = 2 * (c0 + i) - p, k1 = k0 + 1;
+                const float g0 = (k0 >= 0 && k0 < prm.ntaps) ? __ldg(prm.g + k0) : 0.0f;
+                const float g1 = (k1 >= 0 && k1 < prm.ntaps) ? __ldg(prm.g + k1) : 0.0f;
+                if (prm.flags & 1) split2(g1, g0, hi[i], lo[i]);
+                else split2(g0, g1, hi[i], lo[i]);
+            }
+            tmem_st8(lane_addr + (uint32_t)c0, hi);
+            tmem_st8(lane_addr + (uint32_t)(K / 2 + c0), lo);
+        }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 4) {
+        // ================================ PRODUCERS ============================================
+        const int tid = threadIdx.x;                                     // 0..127
+        constexpr int F4_PER_BLOCK = COMPLEX ? 64 : 32;                  // float4 per 128-item block
+        const int in_blocks = TILE_BLOCKS + DK - 1;
+        const int nf4 = in_blocks * F4_PER_BLOCK;
+        const float4 *in4 = reinterpret_cast<const float4 *>(prm.in);
+        constexpr long long F4_ITEMS = COMPLEX ? 2 : 4;                  // items per float4
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            unsigned char *st = gen_base + stage * kStageBytes;
+            const long long item0 = (long long)tile * TILE_ITEMS;
+            constexpr int UNROLL = 6;
+            for (int f0 = tid; f0 < nf4; f0 += UNROLL * kNumProducerThreads) {
+                float4 v[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int f = f0 + u * kNumProducerThreads;
+                    const long long it = item0 + (long long)f * F4_ITEMS;
+                    if (f < nf4 && it + F4_ITEMS <= prm.n_in) {
+                        v[u] = __ldg(in4 + (item0 / F4_ITEMS) + f);
+                    } else {
+                        float t[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (f < nf4) {
+                            const float *src = prm.in + (COMPLEX ? 2 : 1) * it;
+                            const long long rem = (prm.n_in - it) * (COMPLEX ? 2 : 1);
+                            for (int e = 0; e < 4; e++) if (e < rem) t[e] = src[e];
+                        }
+                        v[u] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const int f = f0 + u * kNumProducerThreads;
+                    if (f >= nf4) break;
+                    const int bl = f / F4_PER_BLOCK;                     // block within the tile (warp-uniform)
+                    const int fo = f % F4_PER_BLOCK;
+                    if constexpr (COMPLEX) {
+                        // float4 = (re0, im0, re1, im1): samples o = 2*fo, 2*fo+1 of block bl
+                        const int kc = fo >> 5, c16 = (fo & 31) >> 2, w4 = (fo & 3) * 4;
+                        uint32_t rh, rl, ih, il;
+                        split2(v[u].x, v[u].z, rh, rl);
+                        split2(v[u].y, v[u].w, ih, il);
+                        // physical rows: (gamma = bl%8, jb = bl/8) and its alias (gamma+8, jb-1)
+                        const int g0 = bl & 7, jb0 = bl >> 3;
+#pragma unroll
+                        for (int alias = 0; alias < 2; alias++) {
+                            const int gam = alias ? g0 + 8 : g0, jb = alias ? jb0 - 1 : jb0;
+                            if (jb < 0 || jb >= NSEQ || gam >= atoms) continue;
+                            const int jre = 2 * jb, jim = 2 * jb + 1;
+                            unsigned char *rowp = st + kc * chunk_bytes + gam * 1024;
+                            unsigned char *pre = rowp + jre * 128 + ((c16 ^ jre) << 4) + w4;
+                            unsigned char *pim = rowp + jim * 128 + ((c16 ^ jim) << 4) + w4;
+                            *reinterpret_cast<uint32_t *>(pre) = rh;
+                            *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
+                            *reinterpret_cast<uint32_t *>(pim) = ih;
+                            *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
+                        }
+                    } else {
+                        // float4 = 4 consecutive real samples o = 4*fo .. 4*fo+3 of block bl
+                        const int kc = fo >> 4, c16 = (fo & 15) >> 1, w8 = (fo & 1) * 8;
+                        uint32_t h0, l0, h1, l1;
+                        split2(v[u].x, v[u].y, h0, l0);
+                        split2(v[u].z, v[u].w, h1, l1);
+                        const int g0 = bl & 7, j0 = bl >> 3;
+#pragma unroll
+                        for (int alias = 0; alias < 2; alias++) {
+                            const int gam = alias ? g0 + 8 : g0, j = alias ? j0 - 1 : j0;
+                            if (j < 0 || j >= NSEQ || gam >= atoms) continue;
+                            unsigned char *pp = st + kc * chunk_bytes + gam * 1024 + j * 128 + ((c16 ^ j) << 4) + w8;
+                            *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();                     // generic-proxy stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 8) {
+        // ================================ MMA ISSUER ===========================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 64);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, accphase = 0;
+            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), accphase ^ 1);
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sbase = base + stage * kStageBytes;
+                const uint32_t d_tmem = tmem_acc + 64u * acc;
+                uint32_t accum = 0;
+                for (int d = 0; d < DK; d++) {
+#pragma unroll
+                    for (int kc = 0; kc < 2; kc++) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint32_t kcol = (uint32_t)(d * 64 + kc * 32 + ks * 8);       // A column (2 bf16 / column)
+                            const uint32_t boff = (uint32_t)(kc * chunk_bytes + d * 1024 + ks * 32);
+                            const uint64_t bh = make_b_desc(sbase + boff);
+                            const uint64_t bl = make_b_desc(sbase + split_bytes + boff);
+                            umma_ts(d_tmem, tmem + kcol, bh, idesc, accum);                     // g_hi * x_hi
+                            umma_ts(d_tmem, tmem + kcol, bl, idesc, 1u);                        // g_hi * x_lo
+                            umma_ts(d_tmem, tmem + (uint32_t)(K / 2) + kcol, bh, idesc, 1u);    // g_lo * x_hi
+                            accum = 1u;
+                        }
+                    }
+                }
+                umma_commit(empty_bar(stage));       // smem stage may be refilled once the MMAs read it
+                umma_commit(tfull_bar(acc));         // accumulator complete
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; accphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ EPILOGUE =============================================
+        const int q = warp - 4, p = 32 * q + lane;
+        int acc = 0;
+        uint32_t accphase = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+            mbar_wait(tfull_bar(acc), accphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_acc + 64u * acc + ((uint32_t)(32 * q) << 16);
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
+            const long long blk0 = (long long)tile * TILE_BLOCKS;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t *v = half ? v1 : v0;
+#pragma unroll
+                for (int gl = 0; gl < 4; gl++) {
+                    const int gam = half * 4 + gl;
+                    if constexpr (COMPLEX) {
+#pragma unroll
+                        for (int jb = 0; jb < 4; jb++) {
+                            const long long k = (blk0 + gam + 8 * jb) * 128 + p;
+                            if (k < prm.n_out) {
+                                const float2 o = make_float2(__uint_as_float(v[8 * gl + 2 * jb]),
+                                                             __uint_as_float(v[8 * gl + 2 * jb + 1]));
+                                reinterpret_cast<float2 *>(prm.out)[k] = o;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const long long k = (blk0 + gam + 8 * j) * 128 + p;
+                            if (k < prm.n_out) prm.out[k] = __uint_as_float(v[8 * gl + j]);
+                        }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; accphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool fir_tc_supported(const b2s_fir *f) {
+    if (f->decim != 1) return false;
+    if (f->kind != B2S_C32_F32 && f->kind != B2S_F32_F32) return false;
+    return f->ntaps >= 2 && f->ntaps <= 128 * kMaxDK - 127;   // K = 128*DK >= ntaps + 127
+}
+
+int32_t fir_tc_prepare(b2s_fir *f) {
+    b2s_ctx *ctx = f->ctx;
+    if (f->tc_ready) return B2S_OK;
+    if (!fir_tc_supported(f)) return b2s_fail(ctx, B2S_EUNSUPPORTED, "tensor FIR: unsupported plan");
+    // g[t] = taps[N-1-t] already sits behind the phase table of the direct plan (fir_direct_prepare)
+    f->tc_kblocks = (int)ceil_div(f->ntaps + 127, 128);
+    B2S_CUDA(ctx, cudaFuncSetAttribute(fir_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTC));
+    B2S_CUDA(ctx, cudaFuncSetAttribute(fir_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTC));
+    if (const char *e = getenv("B2S_TC_FLAGS")) f->tc_flags = atoi(e);
+    f->tc_ready = true;
+    return B2S_OK;
+}
+
+void fir_tc_release(b2s_fir *f) { f->tc_ready = false; }
+
+int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                      cudaStream_t stream) {
+    b2s_ctx *ctx = f->ctx;
+    if (n_out == 0) return B2S_OK;
+    if (!f->tc_ready) return b2s_fail(ctx, B2S_ESTATE, "tensor FIR not prepared");
+    // vector loads / float2 stores need natural alignment; otherwise use the direct kernel
+    const bool cplx = f->kind == B2S_C32_F32;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & (cplx ? 7 : 3)))
+        return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);
+    TcParams prm;
+    prm.in = (const float *)d_in;
+    prm.out = (float *)d_out;
+    prm.g = f->d_ptaps + (size_t)f->decim * f->Upad;      // plain reversed taps (fir_direct_prepare)
+    prm.n_in = (long long)n_in;
+    prm.n_out = (long long)n_out;
+    prm.ntaps = (int)f->ntaps;
+    prm.DK = f->tc_kblocks;
+    const long long tile_items = cplx ? 32 * 128 : 64 * 128;
+    prm.num_tiles = (int)ceil_div(n_out, (size_t)tile_items);
+    prm.flags = f->tc_flags;
+    const int grid = std::min(prm.num_tiles, ctx->sm_count);
+    if (cplx) fir_tc_kernel<true><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
+    else fir_tc_kernel<false><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
+    B2S_CHECK_LAUNCH(ctx);
+    return B2S_OK;
+}

@@ -72,9 +72,11 @@ typedef struct b2s_slot   b2s_slot;
 
 /* ---- context (replaces runtime::buffer::vulkan::Instance, buffer/vulkan/mod.rs:45-153) -- */
 int32_t     b2s_version(void);
-/* stream == NULL: the context creates its own non-blocking stream.  Otherwise `stream` is a
- * cudaStream_t owned by the caller (e.g. torch's current stream) and all work is ordered on it. */
-int32_t     b2s_ctx_create(int device, void *stream, b2s_ctx **out);
+/* b2s_ctx_create: the context creates (and owns) a non-blocking stream.
+ * b2s_ctx_create_on_stream: `stream` is a cudaStream_t owned by the caller (e.g. torch's current
+ * stream; 0 / NULL means the legacy default stream) and all work is ordered on it. */
+int32_t     b2s_ctx_create(int device, b2s_ctx **out);
+int32_t     b2s_ctx_create_on_stream(int device, void *stream, b2s_ctx **out);
 void        b2s_ctx_destroy(b2s_ctx *ctx);
 const char *b2s_last_error(const b2s_ctx *ctx); /* ctx may be NULL: last global error       */
 int32_t     b2s_ctx_sync(b2s_ctx *ctx);         /* ≙ awaiting the fence, blocks/vulkan.rs:157-162 */

@@ -46,7 +46,7 @@ def test_version_and_errors_without_gpu():
     from futuresdr_b200 import _lib
     assert _lib.lib.b2s_version() == 100
     h = C.c_void_p()
-    rc = _lib.lib.b2s_ctx_create(0, None, C.byref(h))
+    rc = _lib.lib.b2s_ctx_create(0, C.byref(h))
     import torch
     if not torch.cuda.is_available():
         assert rc == _lib.ECUDA and h.value is None

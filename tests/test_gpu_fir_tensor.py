@@ -1,0 +1,98 @@
+"""Parity of the tcgen05 (tensor-core, split-bf16) FIR against the oracle, through the C ABI.
+Same tolerance as the direct path: |y - y_ref| <= 1e-5 * ||taps||_1 * max|x|."""
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import futuresdr_b200 as fb
+    return fb
+
+
+def _noise(rng, n, cplx=True):
+    if cplx:
+        return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    return rng.standard_normal(n).astype(np.float32)
+
+
+def _check(fb, rng, ntaps, n, cplx, cap=None, taps=None):
+    import torch
+    x = _noise(rng, n, cplx)
+    if taps is None:
+        taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    f = fb.FirFilter(taps, sample_dtype=x.dtype, algo=fb.ALGO_TENSOR)
+    assert f.algo == fb.ALGO_TENSOR
+    cap = n if cap is None else cap
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((max(cap, 1),), 3.0, dtype=xd.dtype, device="cuda")[:cap]
+    c, p, st = f.filter(xd, yd)
+    torch.cuda.synchronize()
+    c0, p0, s0, ref = orc.fir(taps, x, cap)
+    assert (c, p, int(st)) == (c0, p0, s0)
+    if p:
+        tol = 1e-5 * float(np.sum(np.abs(taps))) * float(np.max(np.abs(x)))
+        assert np.max(np.abs(yd[:p].cpu().numpy() - ref)) <= tol
+
+
+@pytest.mark.parametrize("ntaps", [2, 3, 31, 64, 128, 129, 130, 200, 256, 257])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_tensor_fir_parity(fb, rng, ntaps, cplx):
+    _check(fb, rng, ntaps, 30000 + ntaps, cplx)
+
+
+def test_tensor_fir_ragged(fb, rng):
+    for n in (256, 257, 300, 4096 + 255, 4097 + 255, 8192 + 254, 123457):
+        for cap in (n, 1, 4095, 4096, 4097):
+            _check(fb, rng, 256, n, True, cap=cap)
+    for n in (8192 + 255, 8193 + 255, 70001):
+        _check(fb, rng, 256, n, False)
+
+
+def test_tensor_fir_many_tiles_multiwave(fb, rng):
+    # > 148 SMs x 4 stages of tiles: exercises the stage / accumulator ring wrap-around
+    _check(fb, rng, 256, 4096 * 1500 + 255 + 17, True)
+    _check(fb, rng, 100, 8192 * 700 + 99 + 5, False)
+
+
+def test_tensor_fir_kaiser_taps_and_impulse(fb, rng):
+    taps = orc.kaiser_lowpass(0.1, 0.02, 1e-4)[:257]
+    _check(fb, rng, taps.size, 50000, True, taps=taps.astype(np.float32))
+    # impulse response == reversed taps placement (exact in bf16 split: 1.0 is exact)
+    import torch
+    n, ntaps = 9000, 256
+    t = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    x = np.zeros(n, np.complex64); x[5000] = 1.0 + 0.5j
+    f = fb.FirFilter(t, algo=fb.ALGO_TENSOR)
+    yd = torch.zeros(n, dtype=torch.complex64, device="cuda")
+    c, p, st = f.filter(torch.from_numpy(x).cuda(), yd)
+    _, _, _, ref = orc.fir(t, x, n)
+    assert np.max(np.abs(yd[:p].cpu().numpy() - ref)) <= 1e-6
+
+
+def test_tensor_unsupported_shapes_are_refused(fb):
+    with pytest.raises(fb.B200SdrError):
+        fb.DecimatingFirFilter(2, np.ones(64, np.float32), algo=fb.ALGO_TENSOR)
+    with pytest.raises(fb.B200SdrError):
+        fb.FirFilter(np.ones(64, np.complex64), algo=fb.ALGO_TENSOR)
+
+
+def test_tensor_vs_direct_full_chunk(fb):
+    """BASELINE chunk size: tensor path == direct path within tolerance on 64 Mi samples."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(0x5EED)
+    n = 64 * 1024 * 1024
+    x = torch.view_as_complex(torch.randn(n + 255, 2, generator=g, device="cuda"))
+    taps = np.random.default_rng(7).uniform(-1, 1, 256).astype(np.float32)
+    ft = fb.FirFilter(taps, algo=fb.ALGO_TENSOR)
+    fd = fb.FirFilter(taps, algo=fb.ALGO_DIRECT)
+    yt = torch.empty(n, dtype=torch.complex64, device="cuda")
+    yd = torch.empty(n, dtype=torch.complex64, device="cuda")
+    assert ft.filter(x, yt)[:2] == (n, n)
+    assert fd.filter(x, yd)[:2] == (n, n)
+    scale = float(np.sum(np.abs(taps))) * float(x.abs().max())
+    assert float((yt - yd).abs().max()) <= 1e-5 * scale
