@@ -1,0 +1,348 @@
+"""Block-level mirror of the reference's hot-path blocks, over device-resident buffers.
+
+Reference interfaces mirrored (names, argument meaning and finish rules):
+  * ``Fir`` / ``FirBuilder``      src/blocks/fir.rs:13-95, :126-233
+  * ``Fft`` / ``FftDirection``    src/blocks/fft.rs:30-221
+  * ``Apply``                     src/blocks/apply.rs:100-131 (closed catalogue of closures)
+  * ``PfbArbResampler``           src/blocks/pfb/arb_resampler.rs:72-231
+  * ``WorkIo``                    src/runtime/work_io.rs:11-34
+  * ``Mocker``                    src/runtime/mocker.rs:33-190 (single-block harness)
+
+A block's ``work(io)`` does what ``Kernel::work`` does: take the input/output slices of its
+ports, call the core, ``consume``/``produce``, set ``io.finished`` by the reference's rule.
+Ports here are device slices (torch CUDA tensors): samples stay in HBM between blocks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, firdes
+from ._lib import lib, check
+from .context import Context, default_context
+from .filters import (ComputationStatus, DecimatingFirFilter, FirFilter, PolyphaseResamplingFir,
+                      _FilterBase)
+
+
+@dataclass
+class WorkIo:
+    """runtime::WorkIo (work_io.rs:11-34)."""
+    call_again: bool = False
+    finished: bool = False
+
+
+def _tdtype(np_dtype):
+    return torch.complex64 if np.dtype(np_dtype) == np.complex64 else torch.float32
+
+
+class Reader:
+    """mocker::Reader<T> (mocker.rs:213-290): a vector that reports finished() == true."""
+
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+        self.data = torch.zeros(0, dtype=_tdtype(dtype), device="cuda")
+        self.pos = 0
+        self._finished = True
+        self.min_items = 1
+
+    def set(self, data):
+        if isinstance(data, torch.Tensor):
+            t = data.to(device="cuda", dtype=_tdtype(self.dtype))
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(data), dtype=self.dtype)).cuda()
+        self.data, self.pos = t.contiguous(), 0
+
+    def slice(self) -> torch.Tensor:
+        return self.data[self.pos:]
+
+    def consume(self, n: int):
+        assert self.pos + n <= self.data.numel()
+        self.pos += n
+
+    def finished(self) -> bool:
+        return self._finished
+
+    def set_min_items(self, n: int):
+        self.min_items = max(self.min_items, n)
+
+
+class Writer:
+    """mocker::Writer<T> (mocker.rs:326-400): a vector with reserved capacity."""
+
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+        self.data = torch.zeros(0, dtype=_tdtype(dtype), device="cuda")
+        self.len = 0
+        self.min_items = 1
+
+    def reserve(self, n: int):
+        self.data = torch.zeros(n, dtype=_tdtype(self.dtype), device="cuda")
+        self.len = 0
+
+    def slice(self) -> torch.Tensor:
+        return self.data[self.len:]
+
+    def produce(self, n: int):
+        assert self.len + n <= self.data.numel()
+        self.len += n
+
+    def get(self) -> torch.Tensor:
+        return self.data[: self.len]
+
+    def set_min_items(self, n: int):
+        self.min_items = max(self.min_items, n)
+
+
+class Block:
+    in_dtype = np.complex64
+    out_dtype = np.complex64
+
+    def _ports(self):
+        self.input = Reader(self.in_dtype)
+        self.output = Writer(self.out_dtype)
+
+    def work(self, io: WorkIo):          # pragma: no cover
+        raise NotImplementedError
+
+
+class Fir(Block):
+    """blocks::Fir (src/blocks/fir.rs:13-95): generic over a ``Filter`` core."""
+
+    def __init__(self, filter: _FilterBase):
+        self.filter = filter
+        self.in_dtype = self.out_dtype = filter.sample_dtype
+        self._ports()
+        self.input.set_min_items(filter.length())            # fir.rs:49
+
+    def n_taps(self) -> int:
+        return self.filter.length()
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()        # fir.rs:81-82
+        consumed, produced, status = self.filter.filter(i, o)
+        self.input.consume(consumed)
+        self.output.produce(produced)
+        if self.input.finished() and status != ComputationStatus.InsufficientOutput:   # fir.rs:89-91
+            io.finished = True
+
+
+class FirBuilder:
+    """blocks::FirBuilder (src/blocks/fir.rs:126-233)."""
+
+    @staticmethod
+    def fir(taps, sample_dtype=np.complex64, ctx: Optional[Context] = None) -> Fir:
+        return Fir(FirFilter(taps, sample_dtype, ctx))
+
+    @staticmethod
+    def decimating(decim: int, sample_dtype=np.complex64, ctx: Optional[Context] = None) -> Fir:
+        taps = firdes.kaiser.lowpass(1.0 / decim, 0.1, 0.0001)                  # fir.rs:154
+        return FirBuilder.decimating_with_taps(decim, taps, sample_dtype, ctx)
+
+    @staticmethod
+    def decimating_with_taps(decim: int, taps, sample_dtype=np.complex64, ctx=None) -> Fir:
+        return Fir(DecimatingFirFilter(decim, taps, sample_dtype, ctx))
+
+    @staticmethod
+    def resampling(interp: int, decim: int, sample_dtype=np.complex64, ctx=None) -> Fir:
+        g = int(np.gcd(interp, decim))                                          # fir.rs:197-199
+        interp, decim = interp // g, decim // g
+        taps = firdes.kaiser.multirate(interp, decim, 12, 0.0001)               # fir.rs:201
+        return FirBuilder.resampling_with_taps(interp, decim, taps, sample_dtype, ctx)
+
+    @staticmethod
+    def resampling_with_taps(interp: int, decim: int, taps, sample_dtype=np.complex64, ctx=None) -> Fir:
+        return Fir(PolyphaseResamplingFir(interp, decim, taps, sample_dtype, ctx))
+
+
+class FftDirection(enum.Enum):
+    """blocks::FftDirection (fft.rs:48-54)."""
+    Forward = 0
+    Inverse = 1
+
+
+class Fft(Block):
+    """blocks::Fft (src/blocks/fft.rs:30-221)."""
+
+    def __init__(self, len: int, direction: FftDirection = FftDirection.Forward, fft_shift: bool = False,
+                 normalize: Optional[float] = None, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.len, self.direction, self.fft_shift, self.normalize = int(len), direction, fft_shift, normalize
+        self._h = C.c_void_p()
+        check(lib.b2s_fft_plan_c32(self.ctx.handle, self.len, int(direction == FftDirection.Inverse),
+                                   int(fft_shift), int(normalize is not None), float(normalize or 0.0),
+                                   C.byref(self._h)), self.ctx.handle)
+        self._ports()
+        self.input.set_min_items(self.len)
+        self.output.set_min_items(self.len)
+
+    @classmethod
+    def with_direction(cls, len, direction):
+        return cls(len, direction)
+
+    @classmethod
+    def with_options(cls, len, direction, fft_shift, normalize):
+        return cls(len, direction, fft_shift, normalize)
+
+    def transform(self, i: torch.Tensor, o: torch.Tensor):
+        """The body of Fft::work on explicit slices. Returns m (= consumed = produced)."""
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        check(lib.b2s_fft_exec(self._h, C.c_void_p(i.data_ptr()), i.numel(), C.c_void_p(o.data_ptr()),
+                               o.numel(), C.byref(c), C.byref(p)), self.ctx.handle)
+        return c.value
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()
+        m = self.transform(i, o) if min(i.numel(), o.numel()) >= self.len else 0
+        if m > 0:
+            self.input.consume(m)
+            self.output.produce(m)
+        if self.input.finished() and m == (m // self.len) * self.len:           # fft.rs:216-218
+            io.finished = True
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_fft_destroy(self._h)
+            self._h = None
+
+
+class ApplyOp(enum.IntEnum):
+    """The closures of the reference graphs that exist as device ops (b2s_op)."""
+    ScaleF32 = _lib.OP_SCALE_F32
+    ScaleC32 = _lib.OP_SCALE_C32
+    QuadDemod = _lib.OP_QUAD_DEMOD
+    NormSqr = _lib.OP_NORM_SQR
+    QuadDemodC32 = _lib.OP_QUAD_DEMOD_C32
+    ExpF32 = _lib.OP_EXP_F32
+    MagC32 = _lib.OP_MAG_C32
+    Log10F32 = _lib.OP_LOG10_F32
+
+
+_APPLY_TYPES = {
+    ApplyOp.ScaleF32: (np.float32, np.float32), ApplyOp.ScaleC32: (np.complex64, np.complex64),
+    ApplyOp.QuadDemod: (np.complex64, np.float32), ApplyOp.NormSqr: (np.complex64, np.float32),
+    ApplyOp.QuadDemodC32: (np.complex64, np.complex64), ApplyOp.ExpF32: (np.float32, np.float32),
+    ApplyOp.MagC32: (np.complex64, np.float32), ApplyOp.Log10F32: (np.float32, np.float32),
+}
+
+
+class Apply(Block):
+    """blocks::Apply (src/blocks/apply.rs:42-131) for the catalogue of closures in ApplyOp.
+    Stateful closures (the FM demodulator's ``last`` sample) keep their state on the device."""
+
+    def __init__(self, op: ApplyOp, param: float = 1.0, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.op = ApplyOp(op)
+        self.in_dtype, self.out_dtype = _APPLY_TYPES[self.op]
+        self._h = C.c_void_p()
+        check(lib.b2s_apply_create(self.ctx.handle, int(self.op), float(param), C.byref(self._h)), self.ctx.handle)
+        self._ports()
+
+    def apply(self, i: torch.Tensor, o: torch.Tensor) -> int:
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        check(lib.b2s_apply_exec(self._h, C.c_void_p(i.data_ptr()), i.numel(), C.c_void_p(o.data_ptr()),
+                                 o.numel(), C.byref(c), C.byref(p)), self.ctx.handle)
+        return c.value
+
+    def reset(self):
+        check(lib.b2s_apply_reset(self._h), self.ctx.handle)
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()
+        i_len = i.numel()
+        m = min(i_len, o.numel())                                               # apply.rs:109
+        if m > 0:
+            self.apply(i, o)
+            self.input.consume(m)
+            self.output.produce(m)
+        if self.input.finished() and m == i_len:                                 # apply.rs:126-128
+            io.finished = True
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_apply_destroy(self._h)
+            self._h = None
+
+
+class PfbArbResampler(Block):
+    """blocks::PfbArbResampler (src/blocks/pfb/arb_resampler.rs:72-231)."""
+
+    def __init__(self, rate: float, taps, num_filters: int, ctx: Optional[Context] = None):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        # validate input (arb_resampler.rs:92-104: the reference asserts)
+        assert rate > 0.0, "PfbArbResampler: resampling rate must be greater than zero"
+        assert taps.size >= num_filters, "PfbArbResampler: prototype filter length must be at least num_filters"
+        assert num_filters != 0, "PfbArbResampler: number of filter banks must be greater than zero"
+        self.ctx = ctx or default_context()
+        self.rate = np.float32(rate)
+        self._h = C.c_void_p()
+        check(lib.b2s_pfbarb_plan_c32(self.ctx.handle, taps.ctypes.data_as(C.POINTER(C.c_float)), taps.size,
+                                      int(num_filters), float(rate), C.byref(self._h)), self.ctx.handle)
+        self._ports()
+        self.output.set_min_items(int(np.ceil(rate)))                           # arb_resampler.rs:109
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()
+        c, p, ca = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
+        check(lib.b2s_pfbarb_exec(self._h, C.c_void_p(i.data_ptr()), i.numel(), C.c_void_p(o.data_ptr()),
+                                  o.numel(), C.byref(c), C.byref(p), C.byref(ca)), self.ctx.handle)
+        ninput = i.numel()
+        self.input.consume(c.value)
+        self.output.produce(p.value)
+        if ca.value:
+            io.call_again = True
+        elif ninput - c.value == 0 and self.input.finished():                    # :208-211, :227-229
+            io.finished = True
+
+    def reset(self):
+        check(lib.b2s_pfbarb_reset(self._h), self.ctx.handle)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_pfbarb_destroy(self._h)
+            self._h = None
+
+
+class Mocker:
+    """runtime::mocker::Mocker (src/runtime/mocker.rs:33-190): run ONE block without a scheduler."""
+
+    def __init__(self, block: Block):
+        self.block = block
+
+    def input(self, data):
+        self.block.input.set(data)
+
+    def init_output(self, n: int):
+        self.block.output.reserve(n)
+
+    def run(self, max_calls: int = 1 << 20):
+        """Loop work() while call_again is set (mocker.rs:159-190)."""
+        calls = 0
+        while True:
+            io = WorkIo()
+            self.block.work(io)
+            calls += 1
+            if not io.call_again or calls >= max_calls:
+                break
+        self.block.filter.ctx.sync() if hasattr(self.block, "filter") else torch.cuda.synchronize()
+        return io
+
+    def run_until_finished(self, max_calls: int = 1 << 20):
+        """Keep calling work() until the block reports finished or makes no progress."""
+        for _ in range(max_calls):
+            before = (self.block.input.pos, self.block.output.len)
+            io = WorkIo()
+            self.block.work(io)
+            if io.finished:
+                break
+            if not io.call_again and (self.block.input.pos, self.block.output.len) == before:
+                break
+        torch.cuda.synchronize()
+        return io
+
+    def output(self) -> torch.Tensor:
+        return self.block.output.get()

@@ -132,10 +132,13 @@ int32_t b2s_memcpy_d2h(b2s_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
 /* ------------------------------------------------------------------------------------------
  * FIR
  * ---------------------------------------------------------------------------------------- */
+// Below ~48 real taps the CUDA-core kernel is already HBM-bound; above it the tcgen05 kernel wins
+// (measured on B200, profiles/).
+static constexpr size_t kTensorMinTaps = 48;
 static void resolve_algo(b2s_fir *f) {
     if (f->algo_req == B2S_ALGO_TENSOR && fir_tc_supported(f)) f->algo = B2S_ALGO_TENSOR;
-    else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= 48 && getenv("B2S_TC_AUTO"))
-        f->algo = B2S_ALGO_TENSOR;   // TODO(bring-up): make unconditional once the tensor path is verified
+    else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= kTensorMinTaps)
+        f->algo = B2S_ALGO_TENSOR;
     else f->algo = B2S_ALGO_DIRECT;
 }
 

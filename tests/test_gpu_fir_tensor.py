@@ -39,7 +39,7 @@ def _check(fb, rng, ntaps, n, cplx, cap=None, taps=None):
         assert np.max(np.abs(yd[:p].cpu().numpy() - ref)) <= tol
 
 
-@pytest.mark.parametrize("ntaps", [2, 3, 31, 64, 128, 129, 130, 200, 256, 257])
+@pytest.mark.parametrize("ntaps", [16, 17, 31, 64, 128, 129, 130, 200, 256, 257])
 @pytest.mark.parametrize("cplx", [True, False])
 def test_tensor_fir_parity(fb, rng, ntaps, cplx):
     _check(fb, rng, ntaps, 30000 + ntaps, cplx)
@@ -79,6 +79,14 @@ def test_tensor_unsupported_shapes_are_refused(fb):
         fb.DecimatingFirFilter(2, np.ones(64, np.float32), algo=fb.ALGO_TENSOR)
     with pytest.raises(fb.B200SdrError):
         fb.FirFilter(np.ones(64, np.complex64), algo=fb.ALGO_TENSOR)
+    with pytest.raises(fb.B200SdrError):       # < 16 taps: split-bf16 error bound too loose, refused
+        fb.FirFilter(np.ones(5, np.float32), algo=fb.ALGO_TENSOR)
+    with pytest.raises(fb.B200SdrError):       # > 257 taps: Toeplitz operand no longer fits TMEM
+        fb.FirFilter(np.ones(300, np.float32), algo=fb.ALGO_TENSOR)
+    # AUTO falls back to the CUDA-core kernel for those shapes
+    assert fb.FirFilter(np.ones(300, np.float32)).algo == fb.ALGO_DIRECT
+    assert fb.FirFilter(np.ones(5, np.float32)).algo == fb.ALGO_DIRECT
+    assert fb.FirFilter(np.ones(256, np.float32)).algo == fb.ALGO_TENSOR
 
 
 def test_tensor_vs_direct_full_chunk(fb):
