@@ -50,52 +50,62 @@ def _taps():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (NVML polled every ~2 ms from a
+    background thread; falls back to one nvidia-smi query if NVML is unavailable)."""
 
     def __init__(self, index=0):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.thread, self.stop_flag = index, None, False
+        self.sm, self.reasons, self.max_sm = [], set(), None
+
+    def _poll(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get_reasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.proc:
-            return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(2)
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(1.0)
+        if self.sm:
+            return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_sm,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+        try:   # fallback: a single nvidia-smi reading right after the region
+            q = "clocks.sm,clocks.max.sm"
+            o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                str(self.index)], capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(o[0]), "sm_max_mhz": float(o[1]), "reasons": [], "samples": 1,
+                    "source": "nvidia-smi after region"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.path)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        return out
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
 
 # ------------------------------------------------------------------------------------------

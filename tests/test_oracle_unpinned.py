@@ -1,0 +1,143 @@
+"""The three rows whose parity is UNPINNED by the reference's own tests (Fft,
+PfbArbResampler, Apply/demod): the C oracle is cross-checked here against independent
+restatements so that a transcription slip in oracle.c does not go unnoticed."""
+import numpy as np
+import pytest
+
+import oracle as orc
+
+
+def test_fft_oracle_vs_numpy(rng):
+    for n in (2, 8, 64, 100, 2048, 4096):       # 100: the direct O(N^2) branch
+        x = (rng.standard_normal(3 * n + 1) + 1j * rng.standard_normal(3 * n + 1)).astype(np.complex64)
+        m, y = orc.fft_block(x, n)
+        assert m == 3 * n
+        X = x[:m].reshape(3, n).astype(np.complex128)
+        assert np.allclose(y.reshape(3, n), np.fft.fft(X, axis=1), atol=2e-6 * np.sqrt(n) * 4, rtol=1e-6)
+        _, y = orc.fft_block(x, n, fft_shift=True)                       # fwd: shift AFTER (fft.rs:196-204)
+        assert np.allclose(y.reshape(3, n), np.fft.fftshift(np.fft.fft(X, axis=1), axes=1), atol=1e-4, rtol=1e-6)
+        _, y = orc.fft_block(x, n, inverse=True)                          # inverse is un-normalised
+        assert np.allclose(y.reshape(3, n), np.fft.ifft(X, axis=1) * n, atol=1e-4, rtol=1e-6)
+        _, y = orc.fft_block(x, n, inverse=True, fft_shift=True, normalize=0.5)   # inv: shift BEFORE (:179-185)
+        ref = np.fft.ifft(np.fft.ifftshift(X, axes=1), axis=1) * n * 0.5
+        assert np.allclose(y.reshape(3, n), ref, atol=1e-4, rtol=1e-6)
+    # capacity limits m (fft.rs:169-170)
+    m, y = orc.fft_block(np.ones(4096 * 3, np.complex64), 4096, out_cap=4096 * 2 + 5)
+    assert m == 8192
+
+
+def test_quad_demod_oracle(rng):
+    x = (rng.standard_normal(1000) + 1j * rng.standard_normal(1000)).astype(np.complex64)
+    y, carry = orc.quad_demod(x)
+    prev = np.concatenate([[0], x[:-1]])
+    assert np.allclose(y, np.angle(x.astype(np.complex128) * np.conj(prev)), atol=2e-6)
+    assert carry == (float(x[-1].real), float(x[-1].imag))
+    y2a, c = orc.quad_demod(x[:300])
+    y2b, _ = orc.quad_demod(x[300:], c)
+    assert np.array_equal(np.concatenate([y2a, y2b]), y)                  # carry == closure state
+
+
+class PyPfbArb:
+    """Line-by-line Python transcription of arb_resampler.rs + window_buffer.rs + utilities.rs
+    (independent of oracle.c; numpy float32 scalars force f32 rounding after every operation)."""
+
+    def __init__(self, rate, taps, nf):
+        f32 = np.float32
+        self.nf = nf
+        T = int(np.ceil(f32(len(taps)) / f32(nf)))
+        self.T = T
+        self.arms = []
+        for i in range(nf):
+            a = list(taps[i::nf])
+            a += [0.0] * (T - len(a))
+            self.arms.append(np.array(a, np.float32))
+        self.circ = np.zeros(2 * T, np.complex64)
+        self.start, self.missing = 0, T
+        self.rate, self.delay = f32(rate), f32(1.0) / f32(rate)
+        self.tau = f32(0); self.bf = f32(0); self.base = 0; self.mu = f32(0)
+        self.boundary = False
+        self.buff = [np.complex64(0), np.complex64(0)]
+
+    def push(self, s):
+        idx = (self.start - self.missing) % self.T
+        self.circ[idx] = s; self.circ[idx + self.T] = s
+        self.missing = max(self.missing - 1, 0)
+        self.start = (self.start + 1) % self.T
+
+    def filt(self, arm):
+        win = self.circ[self.start:self.start + self.T]
+        re = np.float32(0); im = np.float32(0)
+        a = self.arms[arm]
+        for t in range(self.T):
+            tap = a[self.T - 1 - t]
+            re = np.float32(re + np.float32(win[t].real * tap)); im = np.float32(im + np.float32(win[t].imag * tap))
+        return re, im
+
+    def upd(self):
+        f32 = np.float32
+        self.tau = f32(self.tau + self.delay)
+        self.bf = f32(self.tau * f32(self.nf))
+        self.base = int(np.floor(self.bf))
+        self.mu = f32(self.bf - f32(self.base))
+
+    def blend(self):
+        f32 = np.float32
+        a = f32(f32(1.0) - self.mu)
+        (r0, i0), (r1, i1) = self.buff
+        return complex(f32(f32(a * r0) + f32(self.mu * r1)), f32(f32(a * i0) + f32(self.mu * i1)))
+
+    def consume_single(self, s, out):
+        self.push(s)
+        while self.base < self.nf:
+            if self.boundary:
+                self.buff[1] = self.filt(0)
+                out.append(self.blend()); self.upd(); self.boundary = False
+            else:
+                self.buff[0] = self.filt(self.base)
+                if self.base == self.nf - 1:
+                    self.boundary = True; self.base = self.nf
+                else:
+                    self.buff[1] = self.filt(self.base + 1)
+                    out.append(self.blend()); self.upd()
+        self.tau = np.float32(self.tau - np.float32(1.0))
+        self.bf = np.float32(self.bf - np.float32(self.nf))
+        self.base -= self.nf
+
+    def run(self, x):
+        out, pos = [], 0
+        while self.missing and pos < len(x):
+            self.push(x[pos]); pos += 1
+        for s in x[pos:]:
+            self.consume_single(s, out)
+        return np.array(out, np.complex64)
+
+
+@pytest.mark.parametrize("rate,nf,ntaps", [(1.5, 4, 8), (0.768, 8, 37), (2.3, 5, 23), (0.25, 4, 16)])
+def test_pfbarb_oracle_vs_python_transcription(rng, rate, nf, ntaps):
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    x = (rng.standard_normal(700) + 1j * rng.standard_normal(700)).astype(np.complex64)
+    a = orc.PfbArb(rate, taps, nf).run(x)
+    b = PyPfbArb(rate, taps, nf).run(x)
+    assert a.size == b.size and a.size > 0
+    assert np.array_equal(a, b)                     # same f32 operation order -> bit-exact
+    # call pattern independence (state machine carried across work() calls)
+    o = orc.PfbArb(rate, taps, nf)
+    parts, pos = [], 0
+    for step in (1, 2, 5, 100, 3, 10 ** 6):
+        while True:
+            c, p, ca, out = o.work(x[pos:pos + step], 1 << 16)
+            parts.append(out); pos += c
+            if not ca or c == 0:
+                break
+    assert np.array_equal(np.concatenate(parts), a)
+
+
+def test_pfbarb_window_fill_quirk_is_reproduced():
+    # window_buffer.rs:24-32 while filling writes sample j at slot (start_idx - missing) mod L,
+    # i.e. 0, 2, 4, ... (not an append).  With an impulse as 2nd input sample and T = 4 the
+    # impulse lands in slot 2 of the first window, and the first output shows tap arm[...][T-1-2].
+    taps = np.arange(1, 17, dtype=np.float32)       # 4 arms x 4 taps
+    x = np.zeros(12, np.complex64); x[1] = 1.0
+    y = orc.PfbArb(1.0, taps, 4).run(x)
+    ref = PyPfbArb(1.0, taps, 4).run(x)
+    assert np.array_equal(y, ref) and y.size > 0
