@@ -109,17 +109,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// f32 pair -> packed bf16x2 {lo16 = a, hi16 = b}, round-to-nearest-even
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
+// f32 pair -> packed bf16x2 {lo16 = a, hi16 = b}, round-to-nearest-even, on the INTEGER pipes.
+// (cvt.rn.bf16x2.f32 is an XU-pipe instruction, 16 lanes/clk/SM: with 4 conversions per loaded
+// float4 it was the busiest unit of the kernel -- ncu: sm__inst_executed_pipe_xu 91 %.)
+// RNE on the bit pattern: r = u + 0x7FFF + ((u >> 16) & 1); bf16 = r >> 16.  Identical to
+// cvt.rn for every finite input (inf stays inf; NaN payloads may change, samples are finite).
+__device__ __forceinline__ uint32_t rne_bias(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return u + 0x7FFFu + ((u >> 16) & 1u);
 }
 // split (a, b) into bf16 hi pair and bf16 lo pair:  x ~= hi + lo
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    hi = pack_bf16x2(a, b);
-    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
-    lo = pack_bf16x2(a - ah, b - bh);
+    const uint32_t ra = rne_bias(a), rb = rne_bias(b);
+    hi = __byte_perm(ra, rb, 0x7632);                               // {rb.hi16, ra.hi16}
+    const float ah = __uint_as_float(ra & 0xffff0000u), bh = __uint_as_float(rb & 0xffff0000u);
+    lo = __byte_perm(rne_bias(a - ah), rne_bias(b - bh), 0x7632);
 }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart

@@ -1,0 +1,130 @@
+"""Secondary measurements for the non-headline BASELINE configs (parity-tested elsewhere; these
+are NOT bench.py lines): per-kernel device-resident throughput with CUDA events, reported as
+Msamples/s (input samples) and algorithmic GB/s vs the HBM peak.  Run under gpurun.
+
+    python scripts/bench_configs.py [--quick]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import futuresdr_b200 as fb  # noqa: E402
+from futuresdr_b200 import blocks as B  # noqa: E402
+
+PEAK = 6650.0
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def report(name, n_in, bytes_alg, sec, extra=""):
+    gbs = bytes_alg / sec / 1e9
+    print(json.dumps({"kernel": name, "Msamples_s": round(n_in / sec / 1e6, 1), "ms": round(sec * 1e3, 4),
+                      "alg_GBs": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 4), "note": extra}), flush=True)
+
+
+def main():
+    quick = "--quick" in sys.argv
+    n = (16 if quick else 64) * 1024 * 1024
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.view_as_complex(torch.randn(n + 4096, 2, generator=g, device="cuda"))
+    y = torch.empty(n + 4096, dtype=torch.complex64, device="cuda")
+    rng = np.random.default_rng(7)
+
+    # FIR tap sweep, direct vs tensor
+    for ntaps in (8, 16, 32, 64, 128, 256):
+        taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+        for algo, nm in ((fb.ALGO_DIRECT, "direct"), (fb.ALGO_TENSOR, "tensor")):
+            if algo == fb.ALGO_TENSOR and ntaps < 16:
+                continue
+            f = fb.FirFilter(taps, algo=algo)
+            sec = timeit(lambda: f.filter(x[: n + ntaps - 1], y[:n]))
+            report(f"fir_c32_{ntaps}taps_{nm}", n, 16 * n, sec)
+    # 1024-tap (config 5 per-GPU kernel)
+    taps = rng.uniform(-1, 1, 1024).astype(np.float32)
+    f = fb.FirFilter(taps)
+    nn = n // 4
+    sec = timeit(lambda: f.filter(x[: nn + 1023], y[:nn]), iters=3, warm=1)
+    report("fir_c32_1024taps_auto", nn, 16 * nn, sec, extra=f"algo={f.algo}")
+    # f32 x f32 64 taps (perf/fir config-1 kernel)
+    xr = torch.view_as_real(x).reshape(-1)[: 2 * n]
+    yr = torch.view_as_real(y).reshape(-1)[: 2 * n]
+    t64 = rng.random(64).astype(np.float32)
+    for algo, nm in ((fb.ALGO_DIRECT, "direct"), (fb.ALGO_TENSOR, "tensor")):
+        f = fb.FirFilter(t64, sample_dtype=np.float32, algo=algo)
+        sec = timeit(lambda: f.filter(xr, yr[: 2 * n - 63]))
+        report(f"fir_f32_64taps_{nm}", 2 * n, 8 * 2 * n, sec)
+
+    # config 3 pieces: decimator /4 (52 taps) -> quad demod -> PfbArb 0.768
+    dec = B.FirBuilder.decimating(4)
+    sec = timeit(lambda: dec.filter.filter(x[:n], y[: n // 4]))
+    report("decim4_52taps_c32", n, 8 * n + 8 * (n // 4), sec)
+    n4 = n // 4
+    dem = B.Apply(B.ApplyOp.QuadDemodC32)
+    z = torch.empty(n4, dtype=torch.complex64, device="cuda")
+    sec = timeit(lambda: dem.apply(y[:n4], z))
+    report("quad_demod_c32", n4, 16 * n4, sec)
+    demf = B.Apply(B.ApplyOp.QuadDemod)
+    zf = torch.empty(n4, dtype=torch.float32, device="cuda")
+    sec = timeit(lambda: demf.apply(y[:n4], zf))
+    report("quad_demod_f32", n4, 12 * n4, sec)
+    import oracle as orc
+    ptaps = (orc.kaiser_lowpass(0.4 / 32, 0.1 / 32, 1e-3) * 32).astype(np.float32)[: 32 * 16]
+    pfb = B.PfbArbResampler(0.768, ptaps, 32)
+    w = torch.empty(int(n4 * 0.8) + 1024, dtype=torch.complex64, device="cuda")
+
+    def run_pfb():
+        pfb.input.set(z)
+        pfb.output.data, pfb.output.len = w, 0
+        io = B.WorkIo()
+        pfb.work(io)
+        if io.call_again:
+            pfb.input.data = z
+            pfb.input.pos = pfb.input.pos
+            pfb.work(B.WorkIo())
+    t0 = time.perf_counter()
+    sec = timeit(run_pfb, iters=3, warm=1)
+    report("pfbarb_0.768_32x16", n4, 8 * n4 + 8 * int(n4 * 0.768), sec, extra="includes the host timing-recurrence replay")
+
+    # config 4: FFT 4096
+    for nfft_size in (64, 1024, 2048, 4096, 8192, 16384):
+        fft = B.Fft(nfft_size)
+        sec = timeit(lambda: fft.transform(x[:n], y[:n]))
+        report(f"fft_{nfft_size}_fwd", n, 16 * n, sec)
+    fft = B.Fft.with_options(4096, B.FftDirection.Forward, True, 1.0 / 4096)
+    sec = timeit(lambda: fft.transform(x[:n], y[:n]))
+    report("fft_4096_fwd_shift_norm", n, 16 * n, sec)
+    # rational resampler 3/2 (72 taps) and 48/125
+    for L, M in ((3, 2), (48, 125)):
+        r = B.FirBuilder.resampling(L, M)
+        cap = n // 4 * L // M + L
+        sec = timeit(lambda: r.filter.filter(x[: n // 4], y[:cap]), iters=5)
+        report(f"resamp_{L}_{M}_c32", n // 4, 8 * (n // 4) + 8 * ((n // 4) * L // M), sec)
+    # element-wise scale (the Vulkan/wgpu shader)
+    sc = B.Apply(B.ApplyOp.ScaleF32, 12.0)
+    sec = timeit(lambda: sc.apply(xr, yr))
+    report("scale_f32_x12", 2 * n, 8 * 2 * n, sec)
+
+
+if __name__ == "__main__":
+    main()
