@@ -10,7 +10,7 @@ Importing this package loads libb200sdr.so and raises if it is missing: no CPU f
 from ._lib import (  # noqa: F401
     B200SdrError,
     INSUFFICIENT_INPUT, INSUFFICIENT_OUTPUT, BOTH_SUFFICIENT,
-    ALGO_AUTO, ALGO_DIRECT, ALGO_TENSOR,
+    ALGO_AUTO, ALGO_DIRECT, ALGO_TENSOR, ALGO_FFT,
 )
 from .context import Context, default_context  # noqa: F401
 from .filters import (  # noqa: F401

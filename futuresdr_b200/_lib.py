@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libb200sdr.so")
 OK, EINVAL, ECUDA, ENOMEM, EAGAIN, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6
 INSUFFICIENT_INPUT, INSUFFICIENT_OUTPUT, BOTH_SUFFICIENT = 0, 1, 2
 F32_F32, C32_F32, C32_C32 = 0, 1, 2
-ALGO_AUTO, ALGO_DIRECT, ALGO_TENSOR = 0, 1, 2
+ALGO_AUTO, ALGO_DIRECT, ALGO_TENSOR, ALGO_FFT = 0, 1, 2, 3
 (OP_SCALE_F32, OP_SCALE_C32, OP_QUAD_DEMOD, OP_NORM_SQR, OP_QUAD_DEMOD_C32, OP_EXP_F32,
  OP_MAG_C32, OP_LOG10_F32) = range(8)
 

@@ -135,11 +135,23 @@ int32_t b2s_memcpy_d2h(b2s_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
 // Below ~48 real taps the CUDA-core kernel is already HBM-bound; above it the tcgen05 kernel wins
 // (measured on B200, profiles/).
 static constexpr size_t kTensorMinTaps = 48;
+// Long filters (beyond the tensor kernel's 257 taps) go to the overlap-save FFT kernel.
+static constexpr size_t kFftMinTaps = 258;
 static void resolve_algo(b2s_fir *f) {
     if (f->algo_req == B2S_ALGO_TENSOR && fir_tc_supported(f)) f->algo = B2S_ALGO_TENSOR;
+    else if (f->algo_req == B2S_ALGO_FFT && fir_fft_supported(f)) f->algo = B2S_ALGO_FFT;
     else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= kTensorMinTaps)
         f->algo = B2S_ALGO_TENSOR;
+    else if (f->algo_req == B2S_ALGO_AUTO && fir_fft_supported(f) &&
+             (f->ntaps >= kFftMinTaps || (f->kind == B2S_C32_C32 && f->ntaps >= 128)))
+        f->algo = B2S_ALGO_FFT;
     else f->algo = B2S_ALGO_DIRECT;
+}
+
+static int32_t prepare_algo(b2s_fir *f) {
+    if (f->algo == B2S_ALGO_TENSOR) return fir_tc_prepare(f);
+    if (f->algo == B2S_ALGO_FFT) return fir_fft_prepare(f);
+    return B2S_OK;
 }
 
 int32_t b2s_fir_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntaps, size_t decim,
@@ -159,10 +171,8 @@ int32_t b2s_fir_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntap
     int32_t rc = fir_direct_prepare(f);
     if (rc != B2S_OK) { b2s_fir_destroy(f); return rc; }
     resolve_algo(f);
-    if (f->algo == B2S_ALGO_TENSOR) {
-        rc = fir_tc_prepare(f);
-        if (rc != B2S_OK) { b2s_fir_destroy(f); return rc; }
-    }
+    rc = prepare_algo(f);
+    if (rc != B2S_OK) { b2s_fir_destroy(f); return rc; }
     *out = f;
     return B2S_OK;
 }
@@ -181,6 +191,7 @@ void b2s_fir_destroy(b2s_fir *f) {
     DeviceGuard g(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     fir_tc_release(f);
+    fir_fft_release(f);
     if (f->d_ptaps) cudaFree(f->d_ptaps);
     delete f;
 }
@@ -191,15 +202,16 @@ int32_t b2s_fir_set_algo(b2s_fir *f, b2s_algo algo) {
     if (!f) return b2s_fail(nullptr, B2S_EINVAL, "fir is NULL");
     if (algo == B2S_ALGO_TENSOR && !fir_tc_supported(f))
         return b2s_fail(f->ctx, B2S_EUNSUPPORTED,
-                        "tensor algorithm needs real taps and decim == 1 (kind %d, decim %zu)",
-                        (int)f->kind, f->decim);
+                        "tensor algorithm needs real taps, 16..257 of them, and decim == 1 (kind %d, ntaps %zu, decim %zu)",
+                        (int)f->kind, f->ntaps, f->decim);
+    if (algo == B2S_ALGO_FFT && !fir_fft_supported(f))
+        return b2s_fail(f->ctx, B2S_EUNSUPPORTED,
+                        "FFT algorithm needs Complex<f32> samples, 64..2049 taps and decim == 1 (kind %d, ntaps %zu, decim %zu)",
+                        (int)f->kind, f->ntaps, f->decim);
     f->algo_req = algo;
     resolve_algo(f);
-    if (f->algo == B2S_ALGO_TENSOR && !f->tc_ready) {
-        DeviceGuard g(f->ctx->device);
-        return fir_tc_prepare(f);
-    }
-    return B2S_OK;
+    DeviceGuard g(f->ctx->device);
+    return prepare_algo(f);
 }
 int32_t b2s_fir_get_algo(const b2s_fir *f) { return f ? (int32_t)f->algo : B2S_EINVAL; }
 
@@ -220,6 +232,7 @@ static void fir_counts(const b2s_fir *f, size_t n_in, size_t n_out_cap, size_t *
 static int32_t fir_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                           cudaStream_t stream) {
     if (f->algo == B2S_ALGO_TENSOR) return fir_tc_launch(f, d_in, n_in, d_out, n_out, stream);
+    if (f->algo == B2S_ALGO_FFT) return fir_fft_launch(f, d_in, n_in, d_out, n_out, stream);
     return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);
 }
 

@@ -1,0 +1,66 @@
+// fft_common.cuh -- in-register radix-2/4/8/16 forward DFTs and the padded shared-memory index
+// shared by fft.cu (Fft block) and fir_fft.cu (overlap-save FIR).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fftk {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// ---- in-register forward DFTs, natural-order output ------------------------------------------
+template <int R> struct Dft;
+template <> struct Dft<2> {
+    __device__ static __forceinline__ void run(float2 (&v)[2]) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    }
+};
+template <> struct Dft<4> {
+    __device__ static __forceinline__ void run(float2 (&v)[4]) {
+        const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        const float2 t2 = cadd(v[1], v[3]), t3 = mul_mi(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2); v[1] = cadd(t1, t3); v[2] = csub(t0, t2); v[3] = csub(t1, t3);
+    }
+};
+template <> struct Dft<8> {
+    __device__ static __forceinline__ void run(float2 (&v)[8]) {
+        float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4>::run(e); Dft<4>::run(o);
+        constexpr float h = 0.70710678118654752440f;
+        o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));      // * W8^1 = (1-i)/sqrt2
+        o[2] = mul_mi(o[2]);                                                   // * W8^2 = -i
+        o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));     // * W8^3 = (-1-i)/sqrt2
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = cadd(e[k], o[k]); v[k + 4] = csub(e[k], o[k]); }
+    }
+};
+template <> struct Dft<16> {
+    __device__ static __forceinline__ void run(float2 (&v)[16]) {
+        float2 e[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+        Dft<8>::run(e); Dft<8>::run(o);
+        // W16^k = exp(-2 pi i k / 16)
+        constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+        constexpr float h = 0.70710678118654752440f;
+        o[1] = cmul(o[1], make_float2(c1, -s1));
+        o[2] = make_float2(h * (o[2].x + o[2].y), h * (o[2].y - o[2].x));
+        o[3] = cmul(o[3], make_float2(s1, -c1));
+        o[4] = mul_mi(o[4]);
+        o[5] = cmul(o[5], make_float2(-s1, -c1));
+        o[6] = make_float2(h * (o[6].y - o[6].x), -h * (o[6].x + o[6].y));
+        o[7] = cmul(o[7], make_float2(-c1, -s1));
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[k] = cadd(e[k], o[k]); v[k + 8] = csub(e[k], o[k]); }
+    }
+};
+
+__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
+
+
+}  // namespace fftk

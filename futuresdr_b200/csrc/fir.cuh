@@ -19,6 +19,10 @@ struct b2s_fir {
     int tc_kblocks = 0;
     bool tc_ready = false;
     int tc_flags = 0;            // bring-up switches (env B2S_TC_FLAGS)
+
+    // ---- FFT overlap-save form (fir_fft.cu): H[NF] then W_NF[NF]
+    float2 *d_fftH = nullptr;
+    bool fft_ready = false;
 };
 
 // fir_direct.cu
@@ -31,3 +35,9 @@ int32_t fir_tc_prepare(b2s_fir *f);
 int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                       cudaStream_t stream);
 void    fir_tc_release(b2s_fir *f);
+// fir_fft.cu
+bool    fir_fft_supported(const b2s_fir *f);
+int32_t fir_fft_prepare(b2s_fir *f);
+int32_t fir_fft_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                       cudaStream_t stream);
+void    fir_fft_release(b2s_fir *f);
