@@ -76,8 +76,7 @@ __device__ __forceinline__ void fft_pass(const FftArgs &a, const float2 *gin, fl
         if constexpr (NS > 1) {
             const int k = j & (NS - 1);
             constexpr int STEP = N / (NS * R);
-#pragma unroll
-            for (int r = 1; r < R; r++) v[it][r] = cmul(v[it][r], __ldg(a.tw + ((k * r * STEP) & (N - 1))));
+            apply_twiddles<R>(v[it], __ldg(a.tw + k * STEP));
         }
         Dft<R>::run(v[it]);
         const int j0 = (j / NS) * NS * R + (j & (NS - 1));

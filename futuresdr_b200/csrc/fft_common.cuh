@@ -63,4 +63,27 @@ template <> struct Dft<16> {
 __device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 
 
+// v[r] *= w^r for r = 1..R-1, powers built by a log-depth product tree from ONE table load
+// (15 dependent-free complex multiplies instead of 15 scattered 8-byte loads per butterfly: the
+// table loads of a radix-16 pass cost ~16 L1 wavefronts each and made the FFT LSU-bound).
+// Rounding: every power is at most 4 multiplies deep -> |error| <= ~4 ulp of the twiddle.
+template <int R>
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[R], float2 w1) {
+    if constexpr (R >= 2) v[1] = cmul(v[1], w1);
+    if constexpr (R >= 4) {
+        const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+        v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            const float2 w4 = cmul(w2, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+            v[4] = cmul(v[4], w4); v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7);
+            if constexpr (R >= 16) {
+                const float2 w8 = cmul(w4, w4);
+                v[8] = cmul(v[8], w8); v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3)); v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5));
+                v[14] = cmul(v[14], cmul(w8, w6)); v[15] = cmul(v[15], cmul(w8, w7));
+            }
+        }
+    }
+}
+
 }  // namespace fftk

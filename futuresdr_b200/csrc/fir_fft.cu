@@ -51,8 +51,7 @@ __device__ __forceinline__ void ss_pass(LoadF load, StoreF store, const float2 *
         if constexpr (NS > 1) {
             const int k = j & (NS - 1);
             constexpr int STEP = N / (NS * R);
-#pragma unroll
-            for (int r = 1; r < R; r++) v[it][r] = cmul(v[it][r], __ldg(tw + k * r * STEP));
+            apply_twiddles<R>(v[it], __ldg(tw + k * STEP));
         }
         Dft<R>::run(v[it]);
         const int j0 = (j / NS) * NS * R + (j & (NS - 1));

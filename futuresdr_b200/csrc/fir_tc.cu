@@ -28,22 +28,24 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "fir.cuh"
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kNumProducerThreads = 256;
 constexpr int kNumEpilogueThreads = 128;
 constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 416
 constexpr int kProdWarps = kNumProducerThreads / 32;                         // warps 0..7
 constexpr int kEpiWarp0 = kProdWarps;                                        // warps 8..11 (8 % 4 == 0: TMEM lane quarters line up)
 constexpr int kMmaWarp = kEpiWarp0 + 4;                                      // warp 12
-constexpr int kAtomsOut = 8;                 // N = 64 columns = 8 swizzle atoms of 8 rows
+constexpr int kAtomsOut = 16;                // N = 128 columns = 16 swizzle atoms of 8 rows
+constexpr int kNTile = 8 * kAtomsOut;
 constexpr int kMaxDK = 3;                    // K <= 384  (TMEM: K columns of taps + 128 of accumulators)
-constexpr int kSplitBytesMax = (kAtomsOut + kMaxDK - 1) * 1024 * 2;   // per split: 2 K-chunks x 10 atoms
-constexpr int kStageBytes = 2 * kSplitBytesMax;                       // hi + lo = 40 KiB
+constexpr int kSplitBytesMax = (kAtomsOut + kMaxDK - 1) * 1024 * 2;   // per split: 2 K-chunks x 18 atoms
+constexpr int kStageBytes = 2 * kSplitBytesMax;                       // hi + lo = 72 KiB
 constexpr int kSmemTC = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -157,9 +159,14 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// COMPLEX: rows are (stream ri, block b); a tile = 32 blocks x 128 complex samples, column
-//          c = 8*gamma + 2*jb + ri  <->  block b0 + gamma + 8*jb.
-// REAL   : a tile = 64 blocks x 128 samples, column c = 8*gamma + j <-> block b0 + gamma + 8*j.
+// Tile = N_TILE = 128 columns = 16 swizzle atoms of 8 rows.
+// COMPLEX: rows are (stream ri, block b); 64 blocks x 128 complex samples per tile, column
+//          c = 8*gamma + 2*jb + ri  <->  block b0 + gamma + 16*jb   (gamma < 16, jb < 4)
+// REAL   : 128 blocks x 128 samples per tile, column c = 8*gamma + j <-> block b0 + gamma + 16*j.
+// Why N = 128: a tcgen05.mma (M=128, K=16) never takes less than 48 cycles on B200, whatever N
+// (measured, scripts/mma_rate.cu: N<=64 -> 48 cyc, N=128 -> 64, N=256 -> 128), so N = 64 tiles
+// ran the tensor pipe at 2/3 efficiency.  TMEM holds K columns of taps (hi+lo) + accumulators
+// of 128 columns: two accumulators when K <= 256 (ntaps <= 129), one when K = 384.
 // ---------------------------------------------------------------------------------------------
 template <bool COMPLEX>
 __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams prm) {
@@ -180,11 +187,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int DK = prm.DK, K = 128 * DK;
+    const int nacc = (512 - K) / kNTile;             // accumulators that fit next to the taps (1 or 2)
     const int atoms = kAtomsOut + DK - 1;            // physical 8-row atoms per K-chunk
     const int chunk_bytes = atoms * 1024;            // one K-chunk (64 elements) of all rows
     const int split_bytes = 2 * chunk_bytes;
     constexpr int NSEQ = COMPLEX ? 4 : 8;            // interleaved block sub-sequences
-    constexpr int TILE_BLOCKS = 8 * NSEQ;            // 32 / 64 blocks of 128 samples
+    constexpr int TILE_BLOCKS = kAtomsOut * NSEQ;    // 64 / 128 blocks of 128 samples
     constexpr long long TILE_ITEMS = (long long)TILE_BLOCKS * 128;
 
     if (warp == kMmaWarp) {
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
-    const uint32_t tmem_acc = tmem + (uint32_t)K;    // columns [K, K+128): two 64-column accumulators
+    const uint32_t tmem_acc = tmem + (uint32_t)K;    // columns [K, 512): accumulators
 
     // ---- one-time: Toeplitz taps into TMEM (epilogue warps own lanes 32*(warp%4)...)
     if (warp >= kEpiWarp0 && warp < kMmaWarp) {
@@ -227,14 +235,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 
     if (warp < kProdWarps) {
         // ================================ PRODUCERS ============================================
-        // Thread t handles float4 #(t + 256*i), i = 0..8, of the tile's contiguous input span.
+        // Thread t handles float4 #(t + 256*i), i = 0..16, of the tile's contiguous input span.
         // Its position inside a 128-item block is fixed (fo), only the block row changes with i,
-        // so all swizzle arithmetic is per-thread constant.  Loads of tile n+1 are issued into a
-        // second register set before tile n is converted: ~36 KB of HBM reads in flight per SM.
+        // so all swizzle arithmetic is per-thread constant.  A tile is loaded in two halves; the
+        // loads of the next half are issued into a second register set before the current half
+        // is converted, and whole-tile L2 prefetches run two tiles ahead.
         const int tid = threadIdx.x;                                     // 0..255
         constexpr int F4_PER_BLOCK = COMPLEX ? 64 : 32;                  // float4 per 128-item block
         constexpr int ROWS_PER_PASS = kNumProducerThreads / F4_PER_BLOCK; // 4 (complex) / 8 (real) blocks per i
-        constexpr int NLOAD = 9;
+        constexpr int NLOAD_TILE = 17, NH0 = 9, NH1 = 8;                 // i = 0..8 | 9..16
         constexpr long long F4_ITEMS = COMPLEX ? 2 : 4;                  // items per float4
         const int in_blocks = TILE_BLOCKS + DK - 1;
         const int nf4 = in_blocks * F4_PER_BLOCK;
@@ -244,22 +253,24 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         const int kc = COMPLEX ? (fo >> 5) : (fo >> 4);
         const int c16 = COMPLEX ? ((fo & 31) >> 2) : ((fo & 15) >> 1);
         const int wofs = COMPLEX ? (fo & 3) * 4 : (fo & 1) * 8;
-
         const long long tile_in_items = (long long)in_blocks * 128;       // contiguous input span of a tile
-        auto load_tile = [&](int tile, float4 (&v)[NLOAD]) {
+        static_assert(NH0 + NH1 == NLOAD_TILE, "halves");
+
+        // loads i in [I0, I0 + NI) of `tile` into v[0..NI)
+        auto load_half = [&](int tile, int I0, int NI, float4 (&v)[NH0]) {
             const long long item0 = (long long)tile * TILE_ITEMS;
             const float4 *p = in4 + item0 / F4_ITEMS + tid;
             if (item0 + tile_in_items <= prm.n_in) {                     // interior tile (CTA-uniform)
 #pragma unroll
-                for (int i = 0; i < NLOAD; i++)
-                    if (tid + kNumProducerThreads * i < nf4) v[i] = __ldg(p + kNumProducerThreads * i);
+                for (int i = 0; i < NH0; i++)
+                    if (i < NI && tid + kNumProducerThreads * (I0 + i) < nf4) v[i] = __ldg(p + kNumProducerThreads * (I0 + i));
             } else {                                                     // last tile(s): bounds-checked
 #pragma unroll
-                for (int i = 0; i < NLOAD; i++) {
-                    const int f = tid + kNumProducerThreads * i;
+                for (int i = 0; i < NH0; i++) {
+                    const int f = tid + kNumProducerThreads * (I0 + i);
                     const long long it = item0 + (long long)f * F4_ITEMS;
                     float t[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (f < nf4) {
+                    if (i < NI && f < nf4) {
                         const float *src = prm.in + (COMPLEX ? 2 : 1) * it;
                         const long long rem = (prm.n_in - it) * (COMPLEX ? 2 : 1);
                         for (int e = 0; e < 4; e++) if (e < rem) t[e] = src[e];
@@ -268,9 +279,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                 }
             }
         };
-        // L2 prefetch of a whole tile span, two tiles ahead of the register loads: the LDGs then
-        // hit L2 (~300 cyc) instead of HBM (>1000 cyc under load), so one register set in flight
-        // is enough to keep HBM busy.
         auto prefetch_tile = [&](int tile) {
             if (tile >= prm.num_tiles || tid != 0) return;
             const long long item0 = (long long)tile * TILE_ITEMS;
@@ -282,20 +290,23 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
         };
 
-        auto convert_store = [&](unsigned char *st, const float4 (&v)[NLOAD]) {
+        // convert + store loads i in [I0, I0 + NI)   (I0 is a compile-time constant: 0 or NH0)
+        auto convert_store = [&](unsigned char *st, auto I0c, int NI, const float4 (&v)[NH0]) {
+            constexpr int I0 = decltype(I0c)::value;
             unsigned char *colp = st + kc * chunk_bytes + wofs;
 #pragma unroll
-            for (int i = 0; i < NLOAD; i++) {
+            for (int ii = 0; ii < NH0; ii++) {
+                if (ii >= NI) break;
+                constexpr int dummy = 0; (void)dummy;
+                const int i = I0 + ii;
                 const int bl = rowsel + ROWS_PER_PASS * i;               // block row inside the tile
                 if (bl >= in_blocks) break;
                 if constexpr (COMPLEX) {
-                    // float4 = (re0, im0, re1, im1) ; bl = gamma + 8*jb with gamma = rowsel + 4*(i&1), jb = i>>1
+                    // float4 = (re0, im0, re1, im1); bl = gamma + 16*jb, gamma = rowsel + 4*(i&3), jb = i>>2
                     uint32_t rh, rl, ih, il;
-                    split2(v[i].x, v[i].z, rh, rl);
-                    split2(v[i].y, v[i].w, ih, il);
-                    const int g0 = rowsel + 4 * (i & 1);
-                    constexpr int dummy = 0; (void)dummy;
-                    const int jb0 = i >> 1;
+                    split2(v[ii].x, v[ii].z, rh, rl);
+                    split2(v[ii].y, v[ii].w, ih, il);
+                    const int g0 = rowsel + 4 * (i & 3), jb0 = i >> 2;
                     if (jb0 < NSEQ) {
                         const int jre = 2 * jb0, jim = jre + 1;
                         unsigned char *pre = colp + g0 * 1024 + jre * 128 + ((c16 ^ jre) << 4);
@@ -305,29 +316,29 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                         *reinterpret_cast<uint32_t *>(pim) = ih;
                         *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
                     }
-                    if (jb0 >= 1 && g0 + 8 < atoms) {                    // alias row (gamma+8, jb-1)
+                    if (jb0 >= 1 && g0 + kAtomsOut < atoms) {            // alias row (gamma+16, jb-1)
                         const int jre = 2 * (jb0 - 1), jim = jre + 1;
-                        unsigned char *pre = colp + (g0 + 8) * 1024 + jre * 128 + ((c16 ^ jre) << 4);
-                        unsigned char *pim = colp + (g0 + 8) * 1024 + jim * 128 + ((c16 ^ jim) << 4);
+                        unsigned char *pre = colp + (g0 + kAtomsOut) * 1024 + jre * 128 + ((c16 ^ jre) << 4);
+                        unsigned char *pim = colp + (g0 + kAtomsOut) * 1024 + jim * 128 + ((c16 ^ jim) << 4);
                         *reinterpret_cast<uint32_t *>(pre) = rh;
                         *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
                         *reinterpret_cast<uint32_t *>(pim) = ih;
                         *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
                     }
                 } else {
-                    // float4 = 4 consecutive samples ; bl = gamma + 8*j with gamma = rowsel, j = i
+                    // float4 = 4 consecutive samples; bl = gamma + 16*j, gamma = rowsel + 8*(i&1), j = i>>1
                     uint32_t h0, l0, h1, l1;
-                    split2(v[i].x, v[i].y, h0, l0);
-                    split2(v[i].z, v[i].w, h1, l1);
-                    const int g0 = rowsel, j0 = i;
+                    split2(v[ii].x, v[ii].y, h0, l0);
+                    split2(v[ii].z, v[ii].w, h1, l1);
+                    const int g0 = rowsel + 8 * (i & 1), j0 = i >> 1;
                     if (j0 < NSEQ) {
                         unsigned char *pp = colp + g0 * 1024 + j0 * 128 + ((c16 ^ j0) << 4);
                         *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
                     }
-                    if (j0 >= 1 && g0 + 8 < atoms) {
+                    if (j0 >= 1 && g0 + kAtomsOut < atoms) {
                         const int j = j0 - 1;
-                        unsigned char *pp = colp + (g0 + 8) * 1024 + j * 128 + ((c16 ^ j) << 4);
+                        unsigned char *pp = colp + (g0 + kAtomsOut) * 1024 + j * 128 + ((c16 ^ j) << 4);
                         *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
                     }
@@ -337,52 +348,37 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 
         int stage = 0;
         uint32_t phase = 0;
-        float4 va[NLOAD], vb[NLOAD];
+        float4 va[NH0], vb[NH0];
         int tile = blockIdx.x;
         prefetch_tile(tile + gridDim.x);
-        prefetch_tile(tile + 2 * gridDim.x);
-        if (tile < prm.num_tiles) load_tile(tile, va);
+        if (tile < prm.num_tiles) load_half(tile, 0, NH0, va);
         while (tile < prm.num_tiles) {
-            // ---- even iteration: convert va, prefetch vb
-            {
-                const int next = tile + gridDim.x;
-                prefetch_tile(tile + 3 * gridDim.x);
-                if (next < prm.num_tiles) load_tile(next, vb);
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                convert_store(gen_base + stage * kStageBytes, va);
-                fence_proxy_async();                 // generic-proxy stores -> visible to the MMA (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(stage));
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-                tile = next;
-            }
-            if (tile >= prm.num_tiles) break;
-            // ---- odd iteration: convert vb, prefetch va
-            {
-                const int next = tile + gridDim.x;
-                prefetch_tile(tile + 3 * gridDim.x);
-                if (next < prm.num_tiles) load_tile(next, va);
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                convert_store(gen_base + stage * kStageBytes, vb);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(stage));
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-                tile = next;
-            }
+            const int next = tile + gridDim.x;
+            prefetch_tile(tile + 2 * gridDim.x);
+            load_half(tile, NH0, NH1, vb);                               // second half of this tile
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            unsigned char *st = gen_base + stage * kStageBytes;
+            convert_store(st, std::integral_constant<int, 0>{}, NH0, va);
+            if (next < prm.num_tiles) load_half(next, 0, NH0, va);       // first half of the next tile
+            convert_store(st, std::integral_constant<int, NH0>{}, NH1, vb);
+            fence_proxy_async();                     // generic-proxy stores -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            tile = next;
         }
     } else if (warp == kMmaWarp) {
         // ================================ MMA ISSUER ===========================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, 64);
+            const uint32_t idesc = make_idesc(128, kNTile);
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
             for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), accphase ^ 1);
                 mbar_wait(full_bar(stage), phase);
+                mbar_wait(tempty_bar(acc), accphase ^ 1);
                 tc_fence_after();
                 const uint32_t sbase = base + stage * kStageBytes;
-                const uint32_t d_tmem = tmem_acc + 64u * acc;
+                const uint32_t d_tmem = tmem_acc + (uint32_t)(kNTile * acc);
                 uint32_t accum = 0;
                 for (int d = 0; d < DK; d++) {
 #pragma unroll
@@ -403,7 +399,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                 umma_commit(empty_bar(stage));       // smem stage may be refilled once the MMAs read it
                 umma_commit(tfull_bar(acc));         // accumulator complete
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
-                if (++acc == 2) { acc = 0; accphase ^= 1; }
+                if (++acc == nacc) { acc = 0; accphase ^= 1; }
             }
         }
         __syncwarp();
@@ -415,41 +411,46 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), accphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_acc + 64u * acc + ((uint32_t)(32 * q) << 16);
-            uint32_t v0[32], v1[32];
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
+            const uint32_t taddr = tmem_acc + (uint32_t)(kNTile * acc) + ((uint32_t)(32 * q) << 16);
+            // software-pipelined drain: the load of column chunk c+1 is in flight while chunk c is
+            // stored; the accumulator is released right after the LAST chunk has landed in registers
+            uint32_t v[2][32];
             const long long blk0 = (long long)tile * TILE_BLOCKS;
+            tmem_ld32(taddr, v[0]);
+            tmem_wait_ld();
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t *v = half ? v1 : v0;
+            for (int c = 0; c < 4; c++) {
+                if (c < 3) tmem_ld32(taddr + 32 * (c + 1), v[(c + 1) & 1]);
+                const uint32_t (&vc)[32] = v[c & 1];
 #pragma unroll
                 for (int gl = 0; gl < 4; gl++) {
-                    const int gam = half * 4 + gl;
+                    const int gam = c * 4 + gl;
                     if constexpr (COMPLEX) {
 #pragma unroll
                         for (int jb = 0; jb < 4; jb++) {
-                            const long long k = (blk0 + gam + 8 * jb) * 128 + p;
+                            const long long k = (blk0 + gam + kAtomsOut * jb) * 128 + p;
                             if (k < prm.n_out) {
-                                const float2 o = make_float2(__uint_as_float(v[8 * gl + 2 * jb]),
-                                                             __uint_as_float(v[8 * gl + 2 * jb + 1]));
+                                const float2 o = make_float2(__uint_as_float(vc[8 * gl + 2 * jb]),
+                                                             __uint_as_float(vc[8 * gl + 2 * jb + 1]));
                                 reinterpret_cast<float2 *>(prm.out)[k] = o;
                             }
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const long long k = (blk0 + gam + 8 * j) * 128 + p;
-                            if (k < prm.n_out) prm.out[k] = __uint_as_float(v[8 * gl + j]);
+                            const long long k = (blk0 + gam + kAtomsOut * j) * 128 + p;
+                            if (k < prm.n_out) prm.out[k] = __uint_as_float(vc[8 * gl + j]);
                         }
                     }
                 }
+                if (c < 3) tmem_wait_ld();
+                if (c == 2) {                         // chunk 3 (the last) is now in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
+                }
             }
-            if (++acc == 2) { acc = 0; accphase ^= 1; }
+            if (++acc == nacc) { acc = 0; accphase ^= 1; }
         }
     }
 
@@ -500,7 +501,7 @@ int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, si
     prm.n_out = (long long)n_out;
     prm.ntaps = (int)f->ntaps;
     prm.DK = f->tc_kblocks;
-    const long long tile_items = cplx ? 32 * 128 : 64 * 128;
+    const long long tile_items = cplx ? 64 * 128 : 128 * 128;
     prm.num_tiles = (int)ceil_div(n_out, (size_t)tile_items);
     prm.flags = f->tc_flags;
     const int grid = std::min(prm.num_tiles, ctx->sm_count);
