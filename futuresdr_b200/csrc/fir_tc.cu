@@ -36,11 +36,12 @@ namespace {
 
 constexpr int kStages = 3;
 constexpr int kNumProducerThreads = 256;
-constexpr int kNumEpilogueThreads = 128;
-constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 416
+constexpr int kNumEpilogueThreads = 256;   // 8 warps: two per TMEM lane quarter, 64 columns each
+constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 544
 constexpr int kProdWarps = kNumProducerThreads / 32;                         // warps 0..7
-constexpr int kEpiWarp0 = kProdWarps;                                        // warps 8..11 (8 % 4 == 0: TMEM lane quarters line up)
-constexpr int kMmaWarp = kEpiWarp0 + 4;                                      // warp 12
+constexpr int kEpiWarp0 = kProdWarps;                                        // warps 8..15 (8 % 4 == 0: TMEM lane quarters line up)
+constexpr int kEpiWarps = kNumEpilogueThreads / 32;
+constexpr int kMmaWarp = kEpiWarp0 + kEpiWarps;                              // warp 16
 constexpr int kAtomsOut = 16;                // N = 128 columns = 16 swizzle atoms of 8 rows
 constexpr int kNTile = 8 * kAtomsOut;
 constexpr int kMaxDK = 3;                    // K <= 384  (TMEM: K columns of taps + 128 of accumulators)
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), kProdWarps); mbar_init(empty_bar(s), 1); }
-            for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+            for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     const uint32_t tmem_acc = tmem + (uint32_t)K;    // columns [K, 512): accumulators
 
     // ---- one-time: Toeplitz taps into TMEM (epilogue warps own lanes 32*(warp%4)...)
-    if (warp >= kEpiWarp0 && warp < kMmaWarp) {
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
         const int q = warp - kEpiWarp0, p = 32 * q + lane;   // TMEM lane = output phase p
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
         for (int c0 = 0; c0 < K / 2; c0 += 8) {
@@ -405,49 +406,49 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         __syncwarp();
     } else {
         // ================================ EPILOGUE =============================================
-        const int q = warp - kEpiWarp0, p = 32 * q + lane;
+        // 8 warps: warp w serves TMEM lanes 32*(w%4).. and column half (w-8)/4.  Each warp pulls its
+        // 64 columns with two back-to-back tcgen05.ld, releases the accumulator as soon as they
+        // have landed (the single-accumulator K=384 case stalls the MMA warp until then), and only
+        // then streams the results out: lane p holds y[128*b + p], adjacent columns are (re, im)
+        // of the same block, so every store instruction writes 256 contiguous bytes.
+        const int ew = warp - kEpiWarp0, q = ew & 3, half = ew >> 2, p = 32 * q + lane;
         int acc = 0;
         uint32_t accphase = 0;
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), accphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_acc + (uint32_t)(kNTile * acc) + ((uint32_t)(32 * q) << 16);
-            // software-pipelined drain: the load of column chunk c+1 is in flight while chunk c is
-            // stored; the accumulator is released right after the LAST chunk has landed in registers
+            const uint32_t taddr = tmem_acc + (uint32_t)(kNTile * acc + 64 * half) + ((uint32_t)(32 * q) << 16);
             uint32_t v[2][32];
-            const long long blk0 = (long long)tile * TILE_BLOCKS;
             tmem_ld32(taddr, v[0]);
+            tmem_ld32(taddr + 32, v[1]);
             tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
+            const long long blk0 = (long long)tile * TILE_BLOCKS;
+            const bool interior = (blk0 + TILE_BLOCKS) * 128 <= prm.n_out;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if (c < 3) tmem_ld32(taddr + 32 * (c + 1), v[(c + 1) & 1]);
-                const uint32_t (&vc)[32] = v[c & 1];
+            for (int c = 0; c < 2; c++) {
 #pragma unroll
                 for (int gl = 0; gl < 4; gl++) {
-                    const int gam = c * 4 + gl;
+                    const int gam = half * 8 + c * 4 + gl;
                     if constexpr (COMPLEX) {
+                        float2 *o = reinterpret_cast<float2 *>(prm.out) + (blk0 + gam) * 128 + p;
 #pragma unroll
                         for (int jb = 0; jb < 4; jb++) {
-                            const long long k = (blk0 + gam + kAtomsOut * jb) * 128 + p;
-                            if (k < prm.n_out) {
-                                const float2 o = make_float2(__uint_as_float(vc[8 * gl + 2 * jb]),
-                                                             __uint_as_float(vc[8 * gl + 2 * jb + 1]));
-                                reinterpret_cast<float2 *>(prm.out)[k] = o;
-                            }
+                            const float2 val = make_float2(__uint_as_float(v[c][8 * gl + 2 * jb]),
+                                                           __uint_as_float(v[c][8 * gl + 2 * jb + 1]));
+                            if (interior || (blk0 + gam + kAtomsOut * jb) * 128 + p < prm.n_out)
+                                o[(long long)kAtomsOut * jb * 128] = val;
                         }
                     } else {
+                        float *o = prm.out + (blk0 + gam) * 128 + p;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const long long k = (blk0 + gam + kAtomsOut * j) * 128 + p;
-                            if (k < prm.n_out) prm.out[k] = __uint_as_float(vc[8 * gl + j]);
+                            if (interior || (blk0 + gam + kAtomsOut * j) * 128 + p < prm.n_out)
+                                o[(long long)kAtomsOut * j * 128] = __uint_as_float(v[c][8 * gl + j]);
                         }
                     }
-                }
-                if (c < 3) tmem_wait_ld();
-                if (c == 2) {                         // chunk 3 (the last) is now in registers
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
                 }
             }
             if (++acc == nacc) { acc = 0; accphase ^= 1; }

@@ -84,7 +84,8 @@ def test_tensor_unsupported_shapes_are_refused(fb):
     with pytest.raises(fb.B200SdrError):       # > 257 taps: Toeplitz operand no longer fits TMEM
         fb.FirFilter(np.ones(300, np.float32), algo=fb.ALGO_TENSOR)
     # AUTO falls back to the CUDA-core kernel for those shapes
-    assert fb.FirFilter(np.ones(300, np.float32)).algo == fb.ALGO_DIRECT
+    assert fb.FirFilter(np.ones(300, np.float32)).algo == fb.ALGO_FFT          # long filter: overlap-save
+    assert fb.FirFilter(np.ones(300, np.float32), sample_dtype=np.float32).algo == fb.ALGO_DIRECT
     assert fb.FirFilter(np.ones(5, np.float32)).algo == fb.ALGO_DIRECT
     assert fb.FirFilter(np.ones(256, np.float32)).algo == fb.ALGO_TENSOR
 
