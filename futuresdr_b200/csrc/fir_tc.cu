@@ -35,13 +35,14 @@
 namespace {
 
 constexpr int kStages = 3;
-constexpr int kNumProducerThreads = 256;
+constexpr int kNumProducerThreads = 192;   // 6 warps; 192 is a multiple of the 64 (32) float4 per block
 constexpr int kNumEpilogueThreads = 256;   // 8 warps: two per TMEM lane quarter, 64 columns each
-constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 544
-constexpr int kProdWarps = kNumProducerThreads / 32;                         // warps 0..7
-constexpr int kEpiWarp0 = kProdWarps;                                        // warps 8..15 (8 % 4 == 0: TMEM lane quarters line up)
+constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 480 (<= 512: 128 regs/thread)
+constexpr int kProdWarps = kNumProducerThreads / 32;                         // warps 0..5
+constexpr int kEpiWarp0 = 0;                                                 // warps 0..7 epilogue (warp % 4 = TMEM lane quarter)
 constexpr int kEpiWarps = kNumEpilogueThreads / 32;
-constexpr int kMmaWarp = kEpiWarp0 + kEpiWarps;                              // warp 16
+constexpr int kProdWarp0 = kEpiWarp0 + kEpiWarps;                            // warps 8..13 producers
+constexpr int kMmaWarp = kProdWarp0 + kProdWarps;                            // warp 14
 constexpr int kAtomsOut = 16;                // N = 128 columns = 16 swizzle atoms of 8 rows
 constexpr int kNTile = 8 * kAtomsOut;
 constexpr int kMaxDK = 3;                    // K <= 384  (TMEM: K columns of taps + 128 of accumulators)
@@ -234,17 +235,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     __syncthreads();
     tc_fence_after();
 
-    if (warp < kProdWarps) {
+    if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ================================ PRODUCERS ============================================
-        // Thread t handles float4 #(t + 256*i), i = 0..16, of the tile's contiguous input span.
-        // Its position inside a 128-item block is fixed (fo), only the block row changes with i,
-        // so all swizzle arithmetic is per-thread constant.  A tile is loaded in two halves; the
-        // loads of the next half are issued into a second register set before the current half
-        // is converted, and whole-tile L2 prefetches run two tiles ahead.
-        const int tid = threadIdx.x;                                     // 0..255
+        // Thread t handles float4 #(t + 192*i), i = 0..21, of the tile's contiguous input span.
+        // Its position inside a 128-item block is fixed (fo), only the block row changes with i
+        // (bl = rowsel + ROWS_PER_PASS*i).  A tile is loaded in two halves; the loads of the next
+        // half are issued into a second register set before the current half is converted, and
+        // whole-tile L2 prefetches run two tiles ahead.
+        const int tid = threadIdx.x - 32 * kProdWarp0;                   // 0..191
         constexpr int F4_PER_BLOCK = COMPLEX ? 64 : 32;                  // float4 per 128-item block
-        constexpr int ROWS_PER_PASS = kNumProducerThreads / F4_PER_BLOCK; // 4 (complex) / 8 (real) blocks per i
-        constexpr int NLOAD_TILE = 17, NH0 = 9, NH1 = 8;                 // i = 0..8 | 9..16
+        constexpr int ROWS_PER_PASS = kNumProducerThreads / F4_PER_BLOCK; // 3 (complex) / 6 (real) blocks per i
+        constexpr int NLOAD_TILE = 22, NH0 = 11, NH1 = 11;               // i = 0..10 | 11..21
         constexpr long long F4_ITEMS = COMPLEX ? 2 : 4;                  // items per float4
         const int in_blocks = TILE_BLOCKS + DK - 1;
         const int nf4 = in_blocks * F4_PER_BLOCK;
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         const int wofs = COMPLEX ? (fo & 3) * 4 : (fo & 1) * 8;
         const long long tile_in_items = (long long)in_blocks * 128;       // contiguous input span of a tile
         static_assert(NH0 + NH1 == NLOAD_TILE, "halves");
+        static_assert((TILE_BLOCKS + kMaxDK - 1 + ROWS_PER_PASS - 1) / ROWS_PER_PASS <= NLOAD_TILE, "loads cover the tile");
 
         // loads i in [I0, I0 + NI) of `tile` into v[0..NI)
         auto load_half = [&](int tile, int I0, int NI, float4 (&v)[NH0]) {
@@ -291,25 +293,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
         };
 
-        // convert + store loads i in [I0, I0 + NI)   (I0 is a compile-time constant: 0 or NH0)
-        auto convert_store = [&](unsigned char *st, auto I0c, int NI, const float4 (&v)[NH0]) {
-            constexpr int I0 = decltype(I0c)::value;
+        // convert + store loads i in [I0, I0 + NI)
+        auto convert_store = [&](unsigned char *st, int I0, int NI, const float4 (&v)[NH0]) {
             unsigned char *colp = st + kc * chunk_bytes + wofs;
 #pragma unroll
             for (int ii = 0; ii < NH0; ii++) {
                 if (ii >= NI) break;
-                constexpr int dummy = 0; (void)dummy;
-                const int i = I0 + ii;
-                const int bl = rowsel + ROWS_PER_PASS * i;               // block row inside the tile
+                const int bl = rowsel + ROWS_PER_PASS * (I0 + ii);      // block row inside the tile
                 if (bl >= in_blocks) break;
+                const int g0 = bl & (kAtomsOut - 1), s0 = bl >> 4;       // bl = gamma + 16 * seq
                 if constexpr (COMPLEX) {
-                    // float4 = (re0, im0, re1, im1); bl = gamma + 16*jb, gamma = rowsel + 4*(i&3), jb = i>>2
+                    // float4 = (re0, im0, re1, im1); seq = jb, rows j = 2*jb (re), 2*jb+1 (im)
                     uint32_t rh, rl, ih, il;
                     split2(v[ii].x, v[ii].z, rh, rl);
                     split2(v[ii].y, v[ii].w, ih, il);
-                    const int g0 = rowsel + 4 * (i & 3), jb0 = i >> 2;
-                    if (jb0 < NSEQ) {
-                        const int jre = 2 * jb0, jim = jre + 1;
+                    if (s0 < NSEQ) {
+                        const int jre = 2 * s0, jim = jre + 1;
                         unsigned char *pre = colp + g0 * 1024 + jre * 128 + ((c16 ^ jre) << 4);
                         unsigned char *pim = colp + g0 * 1024 + jim * 128 + ((c16 ^ jim) << 4);
                         *reinterpret_cast<uint32_t *>(pre) = rh;
@@ -317,8 +316,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                         *reinterpret_cast<uint32_t *>(pim) = ih;
                         *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
                     }
-                    if (jb0 >= 1 && g0 + kAtomsOut < atoms) {            // alias row (gamma+16, jb-1)
-                        const int jre = 2 * (jb0 - 1), jim = jre + 1;
+                    if (s0 >= 1 && g0 + kAtomsOut < atoms) {             // alias row (gamma+16, jb-1)
+                        const int jre = 2 * (s0 - 1), jim = jre + 1;
                         unsigned char *pre = colp + (g0 + kAtomsOut) * 1024 + jre * 128 + ((c16 ^ jre) << 4);
                         unsigned char *pim = colp + (g0 + kAtomsOut) * 1024 + jim * 128 + ((c16 ^ jim) << 4);
                         *reinterpret_cast<uint32_t *>(pre) = rh;
@@ -327,18 +326,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                         *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
                     }
                 } else {
-                    // float4 = 4 consecutive samples; bl = gamma + 16*j, gamma = rowsel + 8*(i&1), j = i>>1
+                    // float4 = 4 consecutive samples; seq = j (row inside the atom)
                     uint32_t h0, l0, h1, l1;
                     split2(v[ii].x, v[ii].y, h0, l0);
                     split2(v[ii].z, v[ii].w, h1, l1);
-                    const int g0 = rowsel + 8 * (i & 1), j0 = i >> 1;
-                    if (j0 < NSEQ) {
-                        unsigned char *pp = colp + g0 * 1024 + j0 * 128 + ((c16 ^ j0) << 4);
+                    if (s0 < NSEQ) {
+                        unsigned char *pp = colp + g0 * 1024 + s0 * 128 + ((c16 ^ s0) << 4);
                         *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
                     }
-                    if (j0 >= 1 && g0 + kAtomsOut < atoms) {
-                        const int j = j0 - 1;
+                    if (s0 >= 1 && g0 + kAtomsOut < atoms) {
+                        const int j = s0 - 1;
                         unsigned char *pp = colp + (g0 + kAtomsOut) * 1024 + j * 128 + ((c16 ^ j) << 4);
                         *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
@@ -359,9 +357,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             load_half(tile, NH0, NH1, vb);                               // second half of this tile
             mbar_wait(empty_bar(stage), phase ^ 1);
             unsigned char *st = gen_base + stage * kStageBytes;
-            convert_store(st, std::integral_constant<int, 0>{}, NH0, va);
+            convert_store(st, 0, NH0, va);
             if (next < prm.num_tiles) load_half(next, 0, NH0, va);       // first half of the next tile
-            convert_store(st, std::integral_constant<int, NH0>{}, NH1, vb);
+            convert_store(st, NH0, NH1, vb);
             fence_proxy_async();                     // generic-proxy stores -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
