@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libb200sdr.so")
+# B2S_LIB lets a developer A/B a differently-built library (kernel tuning); default is the in-tree build
+SO_PATH = os.environ.get("B2S_LIB") or os.path.join(_HERE, "libb200sdr.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EAGAIN, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6
 INSUFFICIENT_INPUT, INSUFFICIENT_OUTPUT, BOTH_SUFFICIENT = 0, 1, 2

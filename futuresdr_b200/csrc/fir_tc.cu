@@ -34,21 +34,24 @@
 
 namespace {
 
-constexpr int kStages = 3;
-constexpr int kNumProducerThreads = 192;   // 6 warps; 192 is a multiple of the 64 (32) float4 per block
-constexpr int kNumEpilogueThreads = 256;   // 8 warps: two per TMEM lane quarter, 64 columns each
-constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 32;   // 480 (<= 512: 128 regs/thread)
-constexpr int kProdWarps = kNumProducerThreads / 32;                         // warps 0..5
-constexpr int kEpiWarp0 = 0;                                                 // warps 0..7 epilogue (warp % 4 = TMEM lane quarter)
+constexpr int kStages = 2;                  // bf16 operand stages (72 KiB each)
+constexpr int kRawSlots = 8;                // raw f32 staging ring, 8 KiB per slot (TMA bulk copies)
+constexpr int kRawSlotBytes = 8192;
+constexpr int kNumProducerThreads = 256;    // 8 converter warps
+constexpr int kNumEpilogueThreads = 256;    // 8 warps: two per TMEM lane quarter, 64 columns each
+constexpr int kThreadsTC = kNumProducerThreads + kNumEpilogueThreads + 64;   // + MMA warp + TMA warp = 576
+constexpr int kProdWarps = kNumProducerThreads / 32;
+constexpr int kEpiWarp0 = 0;                // warps 0..7 epilogue (warp % 4 = TMEM lane quarter)
 constexpr int kEpiWarps = kNumEpilogueThreads / 32;
-constexpr int kProdWarp0 = kEpiWarp0 + kEpiWarps;                            // warps 8..13 producers
-constexpr int kMmaWarp = kProdWarp0 + kProdWarps;                            // warp 14
+constexpr int kProdWarp0 = kEpiWarp0 + kEpiWarps;   // warps 8..15 converters
+constexpr int kMmaWarp = kProdWarp0 + kProdWarps;   // warp 16
+constexpr int kTmaWarp = kMmaWarp + 1;              // warp 17
 constexpr int kAtomsOut = 16;                // N = 128 columns = 16 swizzle atoms of 8 rows
 constexpr int kNTile = 8 * kAtomsOut;
 constexpr int kMaxDK = 3;                    // K <= 384  (TMEM: K columns of taps + 128 of accumulators)
 constexpr int kSplitBytesMax = (kAtomsOut + kMaxDK - 1) * 1024 * 2;   // per split: 2 K-chunks x 18 atoms
 constexpr int kStageBytes = 2 * kSplitBytesMax;                       // hi + lo = 72 KiB
-constexpr int kSmemTC = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSmemTC = kStages * kStageBytes + kRawSlots * kRawSlotBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,12 +125,34 @@ __device__ __forceinline__ uint32_t rne_bias(float x) {
     const uint32_t u = __float_as_uint(x);
     return u + 0x7FFFu + ((u >> 16) & 1u);
 }
-// split (a, b) into bf16 hi pair and bf16 lo pair:  x ~= hi + lo
+// f32 pair -> packed bf16x2 on the XU pipe (one instruction)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// split (a, b) into bf16 hi pair and bf16 lo pair:  x ~= hi + lo.
+// B2S_SPLIT_MODE 0: integer pipes only; 1: hi on the XU (cvt), lo on the integer pipes; 2: both on the XU.
+// The producer warps are issue-limited, so trading 7 ALU instructions for 1 XU instruction pays
+// as long as the XU (16 lanes/clk/SM) keeps up: 2 cvt per float4 = ~530 XU cycles per 8192-sample tile.
+#ifndef B2S_SPLIT_MODE
+#define B2S_SPLIT_MODE 2
+#endif
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+#if B2S_SPLIT_MODE == 0
     const uint32_t ra = rne_bias(a), rb = rne_bias(b);
     hi = __byte_perm(ra, rb, 0x7632);                               // {rb.hi16, ra.hi16}
     const float ah = __uint_as_float(ra & 0xffff0000u), bh = __uint_as_float(rb & 0xffff0000u);
     lo = __byte_perm(rne_bias(a - ah), rne_bias(b - bh), 0x7632);
+#else
+    hi = cvt_bf16x2(a, b);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+#if B2S_SPLIT_MODE == 1
+    lo = __byte_perm(rne_bias(a - ah), rne_bias(b - bh), 0x7632);
+#else
+    lo = cvt_bf16x2(a - ah, b - bh);
+#endif
+#endif
 }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
@@ -177,15 +202,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char *gen_base = smem_raw + (base - raw);
-    const uint32_t bar_base = base + kStages * kStageBytes;
-    // barriers: full[kStages], empty[kStages], tfull[2], tempty[2], then tmem address slot
+    const uint32_t raw_base = base + kStages * kStageBytes;           // raw f32 ring
+    unsigned char *raw_gen = gen_base + kStages * kStageBytes;
+    const uint32_t bar_base = raw_base + kRawSlots * kRawSlotBytes;
+    // barriers: full[kStages], empty[kStages], tfull[2], tempty[2], rfull[kRawSlots], rempty[kRawSlots], tmem slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-    volatile uint32_t *tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t *>(gen_base + kStages * kStageBytes + 8 * (2 * kStages + 4));
+    auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + r); };
+    auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kRawSlots + r); };
+    constexpr int kNumBars = 2 * kStages + 4 + 2 * kRawSlots;
+    const uint32_t tmem_slot = bar_base + 8u * kNumBars;
+    volatile uint32_t *tmem_slot_gen = reinterpret_cast<volatile uint32_t *>(
+        gen_base + kStages * kStageBytes + kRawSlots * kRawSlotBytes + 8 * kNumBars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int DK = prm.DK, K = 128 * DK;
@@ -201,6 +231,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         if (lane == 0) {
             for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), kProdWarps); mbar_init(empty_bar(s), 1); }
             for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+            for (int r = 0; r < kRawSlots; r++) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), kProdWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -235,136 +266,140 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     __syncthreads();
     tc_fence_after();
 
-    if (warp >= kProdWarp0 && warp < kMmaWarp) {
-        // ================================ PRODUCERS ============================================
-        // Thread t handles float4 #(t + 192*i), i = 0..21, of the tile's contiguous input span.
-        // Its position inside a 128-item block is fixed (fo), only the block row changes with i
-        // (bl = rowsel + ROWS_PER_PASS*i).  A tile is loaded in two halves; the loads of the next
-        // half are issued into a second register set before the current half is converted, and
-        // whole-tile L2 prefetches run two tiles ahead.
-        const int tid = threadIdx.x - 32 * kProdWarp0;                   // 0..191
-        constexpr int F4_PER_BLOCK = COMPLEX ? 64 : 32;                  // float4 per 128-item block
-        constexpr int ROWS_PER_PASS = kNumProducerThreads / F4_PER_BLOCK; // 3 (complex) / 6 (real) blocks per i
-        constexpr int NLOAD_TILE = 22, NH0 = 11, NH1 = 11;               // i = 0..10 | 11..21
-        constexpr long long F4_ITEMS = COMPLEX ? 2 : 4;                  // items per float4
-        const int in_blocks = TILE_BLOCKS + DK - 1;
-        const int nf4 = in_blocks * F4_PER_BLOCK;
-        const float4 *in4 = reinterpret_cast<const float4 *>(prm.in);
-        const int fo = tid % F4_PER_BLOCK, rowsel = tid / F4_PER_BLOCK;
-        // byte offset inside a 128-byte row before the XOR with the row index
+    // A tile's contiguous input span (TILE_BLOCKS + DK - 1 blocks of 128 items) travels through the raw
+    // ring in slots of 8 KiB = 512 float4 (8 complex blocks / 16 real blocks); 9 slots per tile.
+    constexpr int F4_PER_BLOCK = COMPLEX ? 64 : 32;                       // float4 per 128-item block
+    constexpr int BLOCKS_PER_SLOT = 512 / F4_PER_BLOCK;                   // 8 / 16
+    constexpr int SLOTS_PER_TILE = (TILE_BLOCKS + kMaxDK - 1 + BLOCKS_PER_SLOT - 1) / BLOCKS_PER_SLOT;   // 9
+    constexpr int ITEM_BYTES = COMPLEX ? 8 : 4;
+    const int in_blocks = TILE_BLOCKS + DK - 1;
+
+    if (warp == kTmaWarp) {
+        // ================================ TMA LOADER ===========================================
+        // One thread streams the input with bulk async copies (cp.async.bulk, UBLKCP): the copies
+        // complete on the slot's mbarrier (complete_tx), so HBM latency is absorbed by the 64 KiB
+        // ring and never by a converter warp's registers.
+        if (lane == 0) {
+            int rs = 0;
+            uint32_t rphase = 0;
+            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+                const long long item0 = (long long)tile * TILE_ITEMS;
+#pragma unroll 1
+                for (int s = 0; s < SLOTS_PER_TILE; s++) {
+                    const int blk_first = s * BLOCKS_PER_SLOT;
+                    if (blk_first >= in_blocks) break;
+                    const int nblk = min(BLOCKS_PER_SLOT, in_blocks - blk_first);
+                    const long long it0 = item0 + (long long)blk_first * 128;
+                    long long items = (long long)nblk * 128;
+                    if (it0 + items > prm.n_in) items = prm.n_in - it0;
+                    long long bytes = items > 0 ? ((items * ITEM_BYTES) & ~15ll) : 0;    // whole 16-byte units
+                    mbar_wait(rempty_bar(rs), rphase ^ 1);
+                    if (bytes > 0) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rfull_bar(rs)), "r"((uint32_t)bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(raw_base + rs * kRawSlotBytes), "l"(prm.in + (COMPLEX ? 2 : 1) * it0),
+                                       "r"((uint32_t)bytes), "r"(rfull_bar(rs)) : "memory");
+                    } else {
+                        mbar_arrive(rfull_bar(rs));          // nothing to copy (tile past the end): just hand it over
+                    }
+                    if (++rs == kRawSlots) { rs = 0; rphase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kProdWarp0 && warp < kMmaWarp) {
+        // ================================ CONVERTERS ===========================================
+        // 256 threads; thread t owns float4 #t and #(t+256) of every raw slot: its position inside a
+        // 128-item block is fixed, so the 128B-swizzle arithmetic is per-thread constant.  Per float4:
+        // one LDS.128, the bf16 hi/lo split, and 4 (8 for aliased rows) 32-bit swizzled stores.
+        const int tid = threadIdx.x - 32 * kProdWarp0;                   // 0..255
+        const int fo = tid % F4_PER_BLOCK, rowsel = tid / F4_PER_BLOCK;  // rowsel 0..3 (complex) / 0..7 (real)
+        constexpr int ROWS_PER_PASS = kNumProducerThreads / F4_PER_BLOCK; // blocks covered by 256 threads: 4 / 8
         const int kc = COMPLEX ? (fo >> 5) : (fo >> 4);
         const int c16 = COMPLEX ? ((fo & 31) >> 2) : ((fo & 15) >> 1);
         const int wofs = COMPLEX ? (fo & 3) * 4 : (fo & 1) * 8;
-        const long long tile_in_items = (long long)in_blocks * 128;       // contiguous input span of a tile
-        static_assert(NH0 + NH1 == NLOAD_TILE, "halves");
-        static_assert((TILE_BLOCKS + kMaxDK - 1 + ROWS_PER_PASS - 1) / ROWS_PER_PASS <= NLOAD_TILE, "loads cover the tile");
-
-        // loads i in [I0, I0 + NI) of `tile` into v[0..NI)
-        auto load_half = [&](int tile, int I0, int NI, float4 (&v)[NH0]) {
+        int stage = 0, rs = 0;
+        uint32_t phase = 0, rphase = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             const long long item0 = (long long)tile * TILE_ITEMS;
-            const float4 *p = in4 + item0 / F4_ITEMS + tid;
-            if (item0 + tile_in_items <= prm.n_in) {                     // interior tile (CTA-uniform)
-#pragma unroll
-                for (int i = 0; i < NH0; i++)
-                    if (i < NI && tid + kNumProducerThreads * (I0 + i) < nf4) v[i] = __ldg(p + kNumProducerThreads * (I0 + i));
-            } else {                                                     // last tile(s): bounds-checked
-#pragma unroll
-                for (int i = 0; i < NH0; i++) {
-                    const int f = tid + kNumProducerThreads * (I0 + i);
-                    const long long it = item0 + (long long)f * F4_ITEMS;
-                    float t[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (i < NI && f < nf4) {
-                        const float *src = prm.in + (COMPLEX ? 2 : 1) * it;
-                        const long long rem = (prm.n_in - it) * (COMPLEX ? 2 : 1);
-                        for (int e = 0; e < 4; e++) if (e < rem) t[e] = src[e];
-                    }
-                    v[i] = make_float4(t[0], t[1], t[2], t[3]);
-                }
-            }
-        };
-        auto prefetch_tile = [&](int tile) {
-            if (tile >= prm.num_tiles || tid != 0) return;
-            const long long item0 = (long long)tile * TILE_ITEMS;
-            long long items = prm.n_in - item0;
-            if (items > tile_in_items) items = tile_in_items;
-            const uint32_t bytes = (uint32_t)((items * (COMPLEX ? 8 : 4)) & ~15ll);
-            if (bytes == 0) return;
-            const float *src = prm.in + (COMPLEX ? 2 : 1) * item0;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-        };
-
-        // convert + store loads i in [I0, I0 + NI)
-        auto convert_store = [&](unsigned char *st, int I0, int NI, const float4 (&v)[NH0]) {
-            unsigned char *colp = st + kc * chunk_bytes + wofs;
-#pragma unroll
-            for (int ii = 0; ii < NH0; ii++) {
-                if (ii >= NI) break;
-                const int bl = rowsel + ROWS_PER_PASS * (I0 + ii);      // block row inside the tile
-                if (bl >= in_blocks) break;
-                const int g0 = bl & (kAtomsOut - 1), s0 = bl >> 4;       // bl = gamma + 16 * seq
-                if constexpr (COMPLEX) {
-                    // float4 = (re0, im0, re1, im1); seq = jb, rows j = 2*jb (re), 2*jb+1 (im)
-                    uint32_t rh, rl, ih, il;
-                    split2(v[ii].x, v[ii].z, rh, rl);
-                    split2(v[ii].y, v[ii].w, ih, il);
-                    if (s0 < NSEQ) {
-                        const int jre = 2 * s0, jim = jre + 1;
-                        unsigned char *pre = colp + g0 * 1024 + jre * 128 + ((c16 ^ jre) << 4);
-                        unsigned char *pim = colp + g0 * 1024 + jim * 128 + ((c16 ^ jim) << 4);
-                        *reinterpret_cast<uint32_t *>(pre) = rh;
-                        *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
-                        *reinterpret_cast<uint32_t *>(pim) = ih;
-                        *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
-                    }
-                    if (s0 >= 1 && g0 + kAtomsOut < atoms) {             // alias row (gamma+16, jb-1)
-                        const int jre = 2 * (s0 - 1), jim = jre + 1;
-                        unsigned char *pre = colp + (g0 + kAtomsOut) * 1024 + jre * 128 + ((c16 ^ jre) << 4);
-                        unsigned char *pim = colp + (g0 + kAtomsOut) * 1024 + jim * 128 + ((c16 ^ jim) << 4);
-                        *reinterpret_cast<uint32_t *>(pre) = rh;
-                        *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
-                        *reinterpret_cast<uint32_t *>(pim) = ih;
-                        *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
-                    }
-                } else {
-                    // float4 = 4 consecutive samples; seq = j (row inside the atom)
-                    uint32_t h0, l0, h1, l1;
-                    split2(v[ii].x, v[ii].y, h0, l0);
-                    split2(v[ii].z, v[ii].w, h1, l1);
-                    if (s0 < NSEQ) {
-                        unsigned char *pp = colp + g0 * 1024 + s0 * 128 + ((c16 ^ s0) << 4);
-                        *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
-                        *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
-                    }
-                    if (s0 >= 1 && g0 + kAtomsOut < atoms) {
-                        const int j = s0 - 1;
-                        unsigned char *pp = colp + (g0 + kAtomsOut) * 1024 + j * 128 + ((c16 ^ j) << 4);
-                        *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
-                        *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
-                    }
-                }
-            }
-        };
-
-        int stage = 0;
-        uint32_t phase = 0;
-        float4 va[NH0], vb[NH0];
-        int tile = blockIdx.x;
-        prefetch_tile(tile + gridDim.x);
-        if (tile < prm.num_tiles) load_half(tile, 0, NH0, va);
-        while (tile < prm.num_tiles) {
-            const int next = tile + gridDim.x;
-            prefetch_tile(tile + 2 * gridDim.x);
-            load_half(tile, NH0, NH1, vb);                               // second half of this tile
+            const bool interior = item0 + (long long)in_blocks * 128 <= prm.n_in;
             mbar_wait(empty_bar(stage), phase ^ 1);
-            unsigned char *st = gen_base + stage * kStageBytes;
-            convert_store(st, 0, NH0, va);
-            if (next < prm.num_tiles) load_half(next, 0, NH0, va);       // first half of the next tile
-            convert_store(st, NH0, NH1, vb);
+            unsigned char *colp = gen_base + stage * kStageBytes + kc * chunk_bytes + wofs;
+#pragma unroll
+            for (int s = 0; s < SLOTS_PER_TILE; s++) {
+                if (s * BLOCKS_PER_SLOT >= in_blocks) break;
+                mbar_wait(rfull_bar(rs), rphase);
+                const float4 *raw = reinterpret_cast<const float4 *>(raw_gen + rs * kRawSlotBytes);
+                float4 v[2];
+                v[0] = raw[tid];
+                v[1] = raw[tid + 256];
+                const int rs_cur = rs;
+                if (++rs == kRawSlots) { rs = 0; rphase ^= 1; }
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int bl = s * BLOCKS_PER_SLOT + rowsel + ROWS_PER_PASS * i;   // block row inside the tile
+                    if (bl >= in_blocks) continue;
+                    if (!interior) {
+                        // last tile: the bulk copy moved whole 16-byte units only; the <= 3 trailing floats
+                        // are fetched directly, everything beyond the input is zero
+                        const long long it = item0 + (long long)bl * 128 + (long long)fo * (COMPLEX ? 2 : 4);
+                        const long long gf = it * (COMPLEX ? 2 : 1);                       // global float index of e[0]
+                        const long long total_f = prm.n_in * (COMPLEX ? 2 : 1), copied_f = total_f & ~3ll;
+                        float *e = reinterpret_cast<float *>(&v[i]);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            if (gf + c >= total_f) e[c] = 0.0f;
+                            else if (gf + c >= copied_f) e[c] = prm.in[gf + c];
+                        }
+                    }
+                    // bl = gamma + 16*seq.  complex: gamma = 8*(s&1) + rowsel + 4*i, seq = s>>1 ; real: gamma = rowsel + 8*i, seq = s
+                    const int g0 = bl & (kAtomsOut - 1), s0 = bl >> 4;
+                    if constexpr (COMPLEX) {
+                        uint32_t rh, rl, ih, il;
+                        split2(v[i].x, v[i].z, rh, rl);
+                        split2(v[i].y, v[i].w, ih, il);
+                        if (s0 < NSEQ) {
+                            const int jre = 2 * s0, jim = jre + 1;
+                            unsigned char *pre = colp + g0 * 1024 + jre * 128 + ((c16 ^ jre) << 4);
+                            unsigned char *pim = colp + g0 * 1024 + jim * 128 + ((c16 ^ jim) << 4);
+                            *reinterpret_cast<uint32_t *>(pre) = rh;
+                            *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
+                            *reinterpret_cast<uint32_t *>(pim) = ih;
+                            *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
+                        }
+                        if (s0 >= 1 && g0 + kAtomsOut < atoms) {         // alias row (gamma+16, jb-1)
+                            const int jre = 2 * (s0 - 1), jim = jre + 1;
+                            unsigned char *pre = colp + (g0 + kAtomsOut) * 1024 + jre * 128 + ((c16 ^ jre) << 4);
+                            unsigned char *pim = colp + (g0 + kAtomsOut) * 1024 + jim * 128 + ((c16 ^ jim) << 4);
+                            *reinterpret_cast<uint32_t *>(pre) = rh;
+                            *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
+                            *reinterpret_cast<uint32_t *>(pim) = ih;
+                            *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
+                        }
+                    } else {
+                        uint32_t h0, l0, h1, l1;
+                        split2(v[i].x, v[i].y, h0, l0);
+                        split2(v[i].z, v[i].w, h1, l1);
+                        if (s0 < NSEQ) {
+                            unsigned char *pp = colp + g0 * 1024 + s0 * 128 + ((c16 ^ s0) << 4);
+                            *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
+                        }
+                        if (s0 >= 1 && g0 + kAtomsOut < atoms) {
+                            const int j = s0 - 1;
+                            unsigned char *pp = colp + (g0 + kAtomsOut) * 1024 + j * 128 + ((c16 ^ j) << 4);
+                            *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rempty_bar(rs_cur));          // values consumed: slot may be refilled
+            }
             fence_proxy_async();                     // generic-proxy stores -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == kStages) { stage = 0; phase ^= 1; }
-            tile = next;
         }
     } else if (warp == kMmaWarp) {
         // ================================ MMA ISSUER ===========================================
