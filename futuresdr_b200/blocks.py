@@ -307,6 +307,68 @@ class PfbArbResampler(Block):
             self._h = None
 
 
+class Rotator:
+    """futuredsp::Rotator (crates/futuredsp/src/rotator.rs:13-48): mixer / frequency shifter whose
+    phase recurrence is replayed bit-for-bit (see csrc/rotator.cu)."""
+
+    def __init__(self, phase_incr: float, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self._h = C.c_void_p()
+        check(lib.b2s_rotator_create(self.ctx.handle, float(np.float32(phase_incr)), C.byref(self._h)), self.ctx.handle)
+
+    def rotate(self, input: torch.Tensor, output: torch.Tensor):
+        """Rotator::rotate -> (n, ComputationStatus)."""
+        n, st = C.c_size_t(0), C.c_int32(0)
+        check(lib.b2s_rotator_exec(self._h, C.c_void_p(input.data_ptr()), input.numel(),
+                                   C.c_void_p(output.data_ptr()), output.numel(), C.byref(n), C.byref(st)),
+              self.ctx.handle)
+        return n.value, ComputationStatus(st.value)
+
+    def rotate_inplace(self, buffer: torch.Tensor):
+        self.rotate(buffer, buffer)
+
+    def reset(self):
+        check(lib.b2s_rotator_reset(self._h), self.ctx.handle)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_rotator_destroy(self._h)
+            self._h = None
+
+
+class XlatingFir(Block):
+    """blocks::XlatingFir (src/blocks/xlating_fir.rs:22-126): decimating FIR with band-pass complex
+    taps followed by a Rotator at the output rate."""
+
+    def __init__(self, decimation: int, offset: float, sample_rate: float, taps=None,
+                 ctx: Optional[Context] = None):
+        if taps is None:                                                        # XlatingFir::new (:42-48)
+            assert decimation >= 2, "Xlating FIR: Decimation has to be >= 2"
+            transition_bw = 0.1
+            cutoff = min(0.5 - transition_bw - np.finfo(np.float64).eps, 1.0 / decimation)
+            taps = firdes.kaiser.lowpass(cutoff, transition_bw, 0.0001)
+        assert decimation != 0
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        bpf = np.zeros(taps.size, np.complex64)
+        incr = C.c_float(0.0)
+        check(lib.b2s_xlating_taps(taps.ctypes.data_as(C.POINTER(C.c_float)), taps.size, float(np.float32(offset)),
+                                   float(np.float32(sample_rate)), int(decimation),
+                                   bpf.view(np.float32).ctypes.data_as(C.POINTER(C.c_float)), C.byref(incr)))
+        self.filter = DecimatingFirFilter(decimation, bpf, np.complex64, ctx)
+        self.rotator = Rotator(incr.value, ctx)
+        self._ports()
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()
+        consumed, produced, status = self.filter.filter(i, o)
+        if produced:
+            self.rotator.rotate_inplace(o[:produced])                           # xlating_fir.rs:118
+        self.input.consume(consumed)
+        self.output.produce(produced)
+        if self.input.finished() and status != ComputationStatus.InsufficientOutput:
+            io.finished = True
+
+
 class Mocker:
     """runtime::mocker::Mocker (src/runtime/mocker.rs:33-190): run ONE block without a scheduler."""
 

@@ -25,7 +25,12 @@ struct b2s_fft {
     int log2n = 0;
     int inverse = 0, shift = 0, has_norm = 0;
     float norm = 1.0f;
-    float2 *d_tw = nullptr;     // W_N[k] = exp(-2 pi i k / N), k in [0, N)
+    float2 *d_tw = nullptr;     // W_N[k] = exp(-2 pi i k / N), k in [0, N)  (W_M for Bluestein)
+    // Bluestein (chirp-z) path for lengths that are not a power of two
+    bool bluestein = false;
+    int log2m = 0;              // M = 2^log2m >= 2n - 1
+    float2 *d_chirp = nullptr;  // w[k] = exp(-i pi k^2 / n), k in [0, n)
+    float2 *d_bhat = nullptr;   // FFT_M of the wrapped conjugate chirp, pre-divided by M
 };
 
 namespace {
@@ -99,22 +104,6 @@ __device__ __forceinline__ void fft_pass(const FftArgs &a, const float2 *gin, fl
     if constexpr (!LAST) __syncthreads();
 }
 
-template <int LOG2N> struct Plan;   // radices per pass
-template <> struct Plan<1>  { static constexpr int P = 1, R0 = 2,  R1 = 1,  R2 = 1, R3 = 1; };
-template <> struct Plan<2>  { static constexpr int P = 1, R0 = 4,  R1 = 1,  R2 = 1, R3 = 1; };
-template <> struct Plan<3>  { static constexpr int P = 1, R0 = 8,  R1 = 1,  R2 = 1, R3 = 1; };
-template <> struct Plan<4>  { static constexpr int P = 1, R0 = 16, R1 = 1,  R2 = 1, R3 = 1; };
-template <> struct Plan<5>  { static constexpr int P = 2, R0 = 8,  R1 = 4,  R2 = 1, R3 = 1; };
-template <> struct Plan<6>  { static constexpr int P = 2, R0 = 8,  R1 = 8,  R2 = 1, R3 = 1; };
-template <> struct Plan<7>  { static constexpr int P = 2, R0 = 16, R1 = 8,  R2 = 1, R3 = 1; };
-template <> struct Plan<8>  { static constexpr int P = 2, R0 = 16, R1 = 16, R2 = 1, R3 = 1; };
-template <> struct Plan<9>  { static constexpr int P = 3, R0 = 8,  R1 = 8,  R2 = 8, R3 = 1; };
-template <> struct Plan<10> { static constexpr int P = 3, R0 = 16, R1 = 8,  R2 = 8, R3 = 1; };
-template <> struct Plan<11> { static constexpr int P = 3, R0 = 16, R1 = 16, R2 = 8, R3 = 1; };
-template <> struct Plan<12> { static constexpr int P = 3, R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
-template <> struct Plan<13> { static constexpr int P = 4, R0 = 16, R1 = 8,  R2 = 8, R3 = 8; };
-template <> struct Plan<14> { static constexpr int P = 4, R0 = 16, R1 = 16, R2 = 8, R3 = 8; };
-
 constexpr int kFftThreads = 256;
 
 template <int LOG2N>
@@ -171,6 +160,82 @@ int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
     return B2S_OK;
 }
 
+
+// ---- Bluestein: X[k] = w[k] * sum_n (x[n] w[n]) * conj(w[k-n]),  w[n] = exp(-i pi n^2 / N) ----------
+// One transform per thread group: a = x.w zero-padded to M, A = FFT_M(a), C = A . Bhat,
+// c = IFFT_M(C), X = c . w -- all inside one kernel with the M-point buffer in shared memory.
+struct BsArgs {
+    const float2 *in;
+    float2 *out;
+    const float2 *tw, *chirp, *bhat;
+    long long nfft;
+    int n, inverse, shift, has_norm;
+    float norm;
+};
+
+template <int LOG2M>
+__global__ void __launch_bounds__(kFftThreads) bluestein_kernel(const BsArgs a) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int T = (M / 16 < 1) ? 1 : ((M / 16 > kFftThreads) ? kFftThreads : M / 16);
+    constexpr int FPB = kFftThreads / T;
+    constexpr int MP = M + M / 16;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int t = threadIdx.x % T, fl = threadIdx.x / T;
+    const long long f = (long long)blockIdx.x * FPB + fl;
+    const bool active = f < a.nfft;
+    const long long fc = active ? f : a.nfft - 1;
+    float2 *sm = reinterpret_cast<float2 *>(fsm) + (size_t)fl * MP;
+    const float2 *gin = a.in + fc * a.n;
+    float2 *gout = a.out + fc * a.n;
+    const int n = a.n, half = n / 2;
+    auto st_sm = [&](int idx, float2 v) { sm[pad(idx)] = v; };
+    // forward M-point FFT of a[j] = x'[j] * w[j]  (x' = conj / pre-shifted input for the inverse direction)
+    fft_passes<LOG2M, T>(
+        [&](int idx) {
+            if (idx >= n) return make_float2(0.f, 0.f);
+            const int src = (a.inverse && a.shift) ? (idx + half) % n : idx;        // fft.rs:179-185
+            float2 x = __ldg(gin + src);
+            if (a.inverse) x.y = -x.y;
+            return cmul(x, __ldg(a.chirp + idx));
+        },
+        st_sm, sm, a.tw, t, false);
+    // inverse M-point FFT of A . Bhat as conj(FFT(conj(.))), then the post-chirp
+    fft_passes<LOG2M, T>(
+        [&](int idx) {
+            const float2 y = cmul(sm[pad(idx)], __ldg(a.bhat + idx));
+            return make_float2(y.x, -y.y);
+        },
+        [&](int idx, float2 v) {
+            if (idx >= n || !active) return;
+            float2 y = cmul(make_float2(v.x, -v.y), __ldg(a.chirp + idx));
+            if (a.inverse) y.y = -y.y;
+            if (a.has_norm) { y.x *= a.norm; y.y *= a.norm; }
+            const int dst = (!a.inverse && a.shift) ? (idx + n - half) % n : idx;   // o[k] = X[(k + n/2) % n]  (fft.rs:196-204)
+            gout[dst] = y;
+        },
+        sm, a.tw, t, true);
+}
+
+template <int LOG2M>
+int32_t launch_bluestein(b2s_fft *p, const BsArgs &a, cudaStream_t stream) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int T = (M / 16 < 1) ? 1 : ((M / 16 > kFftThreads) ? kFftThreads : M / 16);
+    constexpr int FPB = kFftThreads / T;
+    constexpr size_t smem = (size_t)FPB * (M + M / 16) * sizeof(float2);
+    auto kern = bluestein_kernel<LOG2M>;
+    if (smem > 48 * 1024) {
+        static thread_local bool set = false;
+        if (!set) {
+            B2S_CUDA(p->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = true;
+        }
+    }
+    const unsigned grid = (unsigned)ceil_div((size_t)a.nfft, (size_t)FPB);
+    kern<<<grid, kFftThreads, smem, stream>>>(a);
+    B2S_CHECK_LAUNCH(p->ctx);
+    return B2S_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -180,24 +245,69 @@ int32_t b2s_fft_plan_c32(b2s_ctx *ctx, size_t n, int32_t inverse, int32_t fft_sh
     if (!ctx || !out) return b2s_fail(ctx, B2S_EINVAL, "b2s_fft_plan_c32: NULL argument");
     *out = nullptr;
     if (n < 2) return b2s_fail(ctx, B2S_EINVAL, "b2s_fft_plan_c32: n must be >= 2");
-    if (n & (n - 1))
-        return b2s_fail(ctx, B2S_EUNSUPPORTED,
-                        "b2s_fft_plan_c32: n = %zu is not a power of two (rustfft handles any n; this build 2..16384)", n);
-    if (n > 16384) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: n = %zu > 16384", n);
+    const bool pow2 = (n & (n - 1)) == 0;
+    if (pow2 && n > 16384) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: n = %zu > 16384", n);
+    if (!pow2 && n > 8192)
+        return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: non-power-of-two n = %zu > 8192 (Bluestein needs M >= 2n-1 <= 16384)", n);
     DeviceGuard g(ctx->device);
     b2s_fft *p = new b2s_fft();
     p->ctx = ctx; p->n = n;
-    while (((size_t)1 << p->log2n) < n) p->log2n++;
     p->inverse = inverse != 0; p->shift = fft_shift != 0; p->has_norm = has_normalize != 0; p->norm = normalize;
-    std::vector<float2> tw(n);
     const double PI = 3.14159265358979323846264338327950288;
-    for (size_t k = 0; k < n; k++) {
-        const double ang = -2.0 * PI * (double)k / (double)n;
+    size_t tw_n = n;
+    if (pow2) {
+        while (((size_t)1 << p->log2n) < n) p->log2n++;
+    } else {
+        p->bluestein = true;
+        while (((size_t)1 << p->log2m) < 2 * n - 1) p->log2m++;
+        tw_n = (size_t)1 << p->log2m;
+    }
+    std::vector<float2> tw(tw_n);
+    for (size_t k = 0; k < tw_n; k++) {
+        const double ang = -2.0 * PI * (double)k / (double)tw_n;
         tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
-    cudaError_t e = cudaMalloc((void **)&p->d_tw, n * sizeof(float2));
+    cudaError_t e = cudaMalloc((void **)&p->d_tw, tw_n * sizeof(float2));
     if (e != cudaSuccess) { delete p; return b2s_fail(ctx, B2S_ENOMEM, "fft twiddles"); }
-    B2S_CUDA(ctx, cudaMemcpyAsync(p->d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    B2S_CUDA(ctx, cudaMemcpyAsync(p->d_tw, tw.data(), tw_n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float2> chirp, bhat;
+    if (p->bluestein) {
+        const size_t M = tw_n;
+        chirp.resize(n); bhat.resize(M);
+        std::vector<double> br(M, 0.0), bi(M, 0.0);
+        for (size_t k = 0; k < n; k++) {
+            const unsigned long long k2 = ((unsigned long long)k * k) % (2ull * n);     // k^2 mod 2n, exact
+            const double ang = -PI * (double)k2 / (double)n;
+            chirp[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+            br[k] = std::cos(ang); bi[k] = -std::sin(ang);                             // conj(w[k])
+            if (k) { br[M - k] = br[k]; bi[M - k] = bi[k]; }
+        }
+        // Bhat = FFT_M(b) / M in f64 (iterative radix-2), once per plan
+        std::vector<double> xr(br), xi(bi);
+        for (size_t i = 1, j = 0; i < M; i++) {
+            size_t bit = M >> 1;
+            for (; j & bit; bit >>= 1) j ^= bit;
+            j ^= bit;
+            if (i < j) { std::swap(xr[i], xr[j]); std::swap(xi[i], xi[j]); }
+        }
+        for (size_t len = 2; len <= M; len <<= 1)
+            for (size_t j = 0; j < len / 2; j++) {
+                const double ang = -2.0 * PI * (double)j / (double)len, wr = std::cos(ang), wi = std::sin(ang);
+                for (size_t s0 = 0; s0 < M; s0 += len) {
+                    const size_t u = s0 + j, v = u + len / 2;
+                    const double tr = xr[v] * wr - xi[v] * wi, ti = xr[v] * wi + xi[v] * wr;
+                    xr[v] = xr[u] - tr; xi[v] = xi[u] - ti; xr[u] += tr; xi[u] += ti;
+                }
+            }
+        for (size_t k = 0; k < M; k++) bhat[k] = make_float2((float)(xr[k] / (double)M), (float)(xi[k] / (double)M));
+        if (cudaMalloc((void **)&p->d_chirp, n * sizeof(float2)) != cudaSuccess ||
+            cudaMalloc((void **)&p->d_bhat, M * sizeof(float2)) != cudaSuccess) {
+            b2s_fft_destroy(p);
+            return b2s_fail(ctx, B2S_ENOMEM, "fft bluestein tables");
+        }
+        B2S_CUDA(ctx, cudaMemcpyAsync(p->d_chirp, chirp.data(), n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        B2S_CUDA(ctx, cudaMemcpyAsync(p->d_bhat, bhat.data(), M * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = p;
     return B2S_OK;
@@ -208,6 +318,8 @@ void b2s_fft_destroy(b2s_fft *p) {
     DeviceGuard g(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     if (p->d_tw) cudaFree(p->d_tw);
+    if (p->d_chirp) cudaFree(p->d_chirp);
+    if (p->d_bhat) cudaFree(p->d_bhat);
     delete p;
 }
 
@@ -224,6 +336,29 @@ int32_t b2s_fft_exec(b2s_fft *p, const void *d_in, size_t n_in, void *d_out, siz
     if (!d_in || !d_out) return b2s_fail(p->ctx, B2S_EINVAL, "b2s_fft_exec: NULL buffer");
     if (d_in == d_out) return b2s_fail(p->ctx, B2S_EINVAL, "b2s_fft_exec: in-place is not supported");
     DeviceGuard g(p->ctx->device);
+    if (p->bluestein) {
+        BsArgs b;
+        b.in = (const float2 *)d_in; b.out = (float2 *)d_out; b.tw = p->d_tw; b.chirp = p->d_chirp; b.bhat = p->d_bhat;
+        b.nfft = (long long)(m / p->n); b.n = (int)p->n;
+        b.inverse = p->inverse; b.shift = p->shift; b.has_norm = p->has_norm; b.norm = p->norm;
+        cudaStream_t bs = p->ctx->stream;
+        switch (p->log2m) {
+            case 2: return launch_bluestein<2>(p, b, bs);
+            case 3: return launch_bluestein<3>(p, b, bs);
+            case 4: return launch_bluestein<4>(p, b, bs);
+            case 5: return launch_bluestein<5>(p, b, bs);
+            case 6: return launch_bluestein<6>(p, b, bs);
+            case 7: return launch_bluestein<7>(p, b, bs);
+            case 8: return launch_bluestein<8>(p, b, bs);
+            case 9: return launch_bluestein<9>(p, b, bs);
+            case 10: return launch_bluestein<10>(p, b, bs);
+            case 11: return launch_bluestein<11>(p, b, bs);
+            case 12: return launch_bluestein<12>(p, b, bs);
+            case 13: return launch_bluestein<13>(p, b, bs);
+            case 14: return launch_bluestein<14>(p, b, bs);
+        }
+        return b2s_fail(p->ctx, B2S_EUNSUPPORTED, "b2s_fft_exec: unsupported Bluestein size");
+    }
     FftArgs a;
     a.in = (const float2 *)d_in; a.out = (float2 *)d_out; a.tw = p->d_tw; a.nfft = (long long)(m / p->n);
     a.inverse = p->inverse; a.shift = p->shift; a.has_norm = p->has_norm; a.norm = p->norm;

@@ -86,4 +86,80 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[R], float2 w1) {
     }
 }
 
+template <int LOG2N> struct Plan;   // radices per pass
+template <> struct Plan<1>  { static constexpr int P = 1, R0 = 2,  R1 = 1,  R2 = 1, R3 = 1; };
+template <> struct Plan<2>  { static constexpr int P = 1, R0 = 4,  R1 = 1,  R2 = 1, R3 = 1; };
+template <> struct Plan<3>  { static constexpr int P = 1, R0 = 8,  R1 = 1,  R2 = 1, R3 = 1; };
+template <> struct Plan<4>  { static constexpr int P = 1, R0 = 16, R1 = 1,  R2 = 1, R3 = 1; };
+template <> struct Plan<5>  { static constexpr int P = 2, R0 = 8,  R1 = 4,  R2 = 1, R3 = 1; };
+template <> struct Plan<6>  { static constexpr int P = 2, R0 = 8,  R1 = 8,  R2 = 1, R3 = 1; };
+template <> struct Plan<7>  { static constexpr int P = 2, R0 = 16, R1 = 8,  R2 = 1, R3 = 1; };
+template <> struct Plan<8>  { static constexpr int P = 2, R0 = 16, R1 = 16, R2 = 1, R3 = 1; };
+template <> struct Plan<9>  { static constexpr int P = 3, R0 = 8,  R1 = 8,  R2 = 8, R3 = 1; };
+template <> struct Plan<10> { static constexpr int P = 3, R0 = 16, R1 = 8,  R2 = 8, R3 = 1; };
+template <> struct Plan<11> { static constexpr int P = 3, R0 = 16, R1 = 16, R2 = 8, R3 = 1; };
+template <> struct Plan<12> { static constexpr int P = 3, R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
+template <> struct Plan<13> { static constexpr int P = 4, R0 = 16, R1 = 8,  R2 = 8, R3 = 8; };
+template <> struct Plan<14> { static constexpr int P = 4, R0 = 16, R1 = 16, R2 = 8, R3 = 8; };
+
+
+// One Stockham pass: loads through `load`, optional CTA barrier (in-place passes), twiddles, DFT,
+// stores through `store`, CTA barrier.
+template <int N, int R, int NS, int T, typename LoadF, typename StoreF>
+__device__ __forceinline__ void ss_pass(LoadF load, StoreF store, const float2 *__restrict__ tw, int t,
+                                        bool sync_between) {
+    constexpr int NB = N / R, ITER = NB / T;
+    static_assert(NB % T == 0 || NB < T, "butterflies must tile the threads");
+    float2 v[ITER][R];
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+        const int j = t + it * T;
+#pragma unroll
+        for (int r = 0; r < R; r++) v[it][r] = load(j + r * NB);
+    }
+    if (sync_between) __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+        const int j = t + it * T;
+        if constexpr (NS > 1) {
+            const int k = j & (NS - 1);
+            constexpr int STEP = N / (NS * R);
+            apply_twiddles<R>(v[it], __ldg(tw + k * STEP));
+        }
+        Dft<R>::run(v[it]);
+        const int j0 = (j / NS) * NS * R + (j & (NS - 1));
+#pragma unroll
+        for (int r = 0; r < R; r++) store(j0 + r * NS, v[it][r]);
+    }
+    __syncthreads();
+}
+
+
+// Runs a whole LOG2N-point forward FFT as Stockham passes through the padded smem buffer `sm`.
+// Pass 0 reads through `first_load(idx)`, the last pass writes through `last_store(idx, v)`, the
+// passes in between read and write `sm`.  first_reads_smem: pass 0's source is `sm` itself.
+template <int LOG2N, int T, typename LoadF, typename StoreF>
+__device__ __forceinline__ void fft_passes(LoadF first_load, StoreF last_store, float2 *sm,
+                                           const float2 *__restrict__ tw, int t, bool first_reads_smem) {
+    constexpr int N = 1 << LOG2N;
+    using PL = Plan<LOG2N>;
+    auto ld_sm = [&](int idx) { return sm[pad(idx)]; };
+    auto st_sm = [&](int idx, float2 v) { sm[pad(idx)] = v; };
+    if constexpr (PL::P == 1) {
+        ss_pass<N, PL::R0, 1, T>(first_load, last_store, tw, t, first_reads_smem);
+    } else if constexpr (PL::P == 2) {
+        ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, first_reads_smem);
+        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, last_store, tw, t, true);
+    } else if constexpr (PL::P == 3) {
+        ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, first_reads_smem);
+        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
+        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, last_store, tw, t, true);
+    } else {
+        ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, first_reads_smem);
+        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
+        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, st_sm, tw, t, true);
+        ss_pass<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T>(ld_sm, last_store, tw, t, true);
+    }
+}
+
 }  // namespace fftk

@@ -32,35 +32,6 @@ struct FftFirArgs {
     int V;              // valid outputs per block
 };
 
-template <int N, int R, int NS, int T, typename LoadF, typename StoreF>
-__device__ __forceinline__ void ss_pass(LoadF load, StoreF store, const float2 *__restrict__ tw, int t,
-                                        bool sync_between) {
-    constexpr int NB = N / R, ITER = NB / T;
-    static_assert(NB % T == 0, "butterflies must tile the threads");
-    float2 v[ITER][R];
-#pragma unroll
-    for (int it = 0; it < ITER; it++) {
-        const int j = t + it * T;
-#pragma unroll
-        for (int r = 0; r < R; r++) v[it][r] = load(j + r * NB);
-    }
-    if (sync_between) __syncthreads();
-#pragma unroll
-    for (int it = 0; it < ITER; it++) {
-        const int j = t + it * T;
-        if constexpr (NS > 1) {
-            const int k = j & (NS - 1);
-            constexpr int STEP = N / (NS * R);
-            apply_twiddles<R>(v[it], __ldg(tw + k * STEP));
-        }
-        Dft<R>::run(v[it]);
-        const int j0 = (j / NS) * NS * R + (j & (NS - 1));
-#pragma unroll
-        for (int r = 0; r < R; r++) store(j0 + r * NS, v[it][r]);
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(kFfThreads) fir_fft_kernel(const FftFirArgs a) {
     constexpr int N = kNF, T = kFfThreads;
     extern __shared__ __align__(16) unsigned char ffsm[];

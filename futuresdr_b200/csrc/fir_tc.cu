@@ -282,8 +282,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         if (lane == 0) {
             int rs = 0;
             uint32_t rphase = 0;
+            const long long tile_in_items = (long long)in_blocks * 128;
+            auto prefetch_tile = [&](int tile) {     // whole-tile L2 prefetch, two tiles ahead of the ring
+                if (tile >= prm.num_tiles) return;
+                const long long i0 = (long long)tile * TILE_ITEMS;
+                long long items = prm.n_in - i0;
+                if (items > tile_in_items) items = tile_in_items;
+                const uint32_t bytes = (uint32_t)((items * ITEM_BYTES) & ~15ll);
+                if (bytes == 0) return;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(prm.in + (COMPLEX ? 2 : 1) * i0), "r"(bytes) : "memory");
+            };
+            prefetch_tile(blockIdx.x + gridDim.x);
             for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
                 const long long item0 = (long long)tile * TILE_ITEMS;
+                prefetch_tile(tile + 2 * gridDim.x);
 #pragma unroll 1
                 for (int s = 0; s < SLOTS_PER_TILE; s++) {
                     const int blk_first = s * BLOCKS_PER_SLOT;
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const int bl = s * BLOCKS_PER_SLOT + rowsel + ROWS_PER_PASS * i;   // block row inside the tile
-                    if (bl >= in_blocks) continue;
+                    if (bl >= in_blocks || (prm.flags & 8)) continue;   // flags bit3: tuning switch, skip conversion
                     if (!interior) {
                         // last tile: the bulk copy moved whole 16-byte units only; the <= 3 trailing floats
                         // are fetched directly, everything beyond the input is zero
@@ -414,7 +426,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                 const uint32_t sbase = base + stage * kStageBytes;
                 const uint32_t d_tmem = tmem_acc + (uint32_t)(kNTile * acc);
                 uint32_t accum = 0;
-                for (int d = 0; d < DK; d++) {
+                for (int d = 0; d < ((prm.flags & 4) ? 0 : DK); d++) {   // flags bit2: tuning switch, skip the MMAs
 #pragma unroll
                     for (int kc = 0; kc < 2; kc++) {
 #pragma unroll
@@ -460,6 +472,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
             const long long blk0 = (long long)tile * TILE_BLOCKS;
             const bool interior = (blk0 + TILE_BLOCKS) * 128 <= prm.n_out;
+            if (prm.flags & 2) goto epi_next;           // tuning switch: skip the global stores
 #pragma unroll
             for (int c = 0; c < 2; c++) {
 #pragma unroll
@@ -484,6 +497,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                     }
                 }
             }
+        epi_next:
             if (++acc == nacc) { acc = 0; accphase ^= 1; }
         }
     }

@@ -21,8 +21,7 @@ struct b2s_resamp {
 namespace {
 
 constexpr int kRsThreads = 256;
-constexpr int kRsPerThread = 4;
-constexpr int kRsTK = kRsThreads * kRsPerThread;
+constexpr int kRsR = 4;          // outputs per thread that share one polyphase bank (tap reuse)
 
 template <typename S> __device__ __forceinline__ S rs_zero();
 template <> __device__ __forceinline__ float rs_zero<float>() { return 0.f; }
@@ -30,33 +29,56 @@ template <> __device__ __forceinline__ float2 rs_zero<float2>() { return make_fl
 __device__ __forceinline__ void rs_mac(float &a, float x, float t) { a = fmaf(x, t, a); }
 __device__ __forceinline__ void rs_mac(float2 &a, float2 x, float t) { a.x = fmaf(x.x, t, a.x); a.y = fmaf(x.y, t, a.y); }
 
+// A CTA produces R*S consecutive outputs, S = L*G >= 256 a multiple of L.  Thread slot tt < S owns
+// the R outputs  k = kb + tt + r*S:  they share the bank (k*M mod L) and their input windows are
+// exactly G*M items apart, so every tap fetched from shared memory feeds R MACs.
 template <typename S, bool TAPS_IN_SMEM>
 __global__ void __launch_bounds__(kRsThreads)
 resamp_kernel(const S *__restrict__ in, S *__restrict__ out, const float *__restrict__ banks, int L, int M,
-              int T, int pitch, long long n_out, int span_max) {
+              int T, int pitch, long long n_out, int G, int span_max) {
     extern __shared__ __align__(16) unsigned char rsm[];
     S *xs = reinterpret_cast<S *>(rsm);
     float *gs = reinterpret_cast<float *>(rsm + (size_t)span_max * sizeof(S));
-    const long long k0 = (long long)blockIdx.x * kRsTK;
-    const long long klast = min(k0 + kRsTK, n_out) - 1;
-    const long long base = k0 * M / L;                         // first input item of the tile
+    const int Sg = L * G;                                       // outputs per r-slab
+    const long long kb = (long long)blockIdx.x * kRsR * Sg;
+    const long long klast = min(kb + (long long)kRsR * Sg, n_out) - 1;
+    const long long base = kb * M / L;                          // first input item of the tile (kb*M/L exact: kb % L == 0)
     const int span = (int)(klast * M / L - base) + T;           // items the tile touches (<= span_max)
     for (int j = threadIdx.x; j < span; j += kRsThreads) xs[j] = in[base + j];
     if (TAPS_IN_SMEM)
         for (int j = threadIdx.x; j < L * pitch; j += kRsThreads) gs[j] = banks[j];
     __syncthreads();
     const float *g = TAPS_IN_SMEM ? gs : banks;
-#pragma unroll
-    for (int i = 0; i < kRsPerThread; i++) {
-        const long long k = k0 + threadIdx.x + i * kRsThreads;
-        if (k > klast) break;
-        const long long km = k * M;
+    const int step = G * M;                                     // input distance between a thread's outputs
+    for (int tt = threadIdx.x; tt < Sg; tt += kRsThreads) {
+        const long long k0 = kb + tt;
+        if (k0 > klast) break;
+        const long long km = (long long)tt * M;                 // (k0 - kb)*M ; kb*M is a multiple of L
         const int bank = (int)(km % L);
-        const int i0 = (int)(km / L - base);
+        const int i0 = (int)(km / L);
         const float *gb = g + bank * pitch;
-        S acc = rs_zero<S>();
-        for (int t = 0; t < T; t++) rs_mac(acc, xs[i0 + t], gb[t]);
-        out[k] = acc;
+        S acc[kRsR];
+#pragma unroll
+        for (int r = 0; r < kRsR; r++) acc[r] = rs_zero<S>();
+        int nr = kRsR;                                          // outputs of this thread inside n_out
+        while (nr > 1 && k0 + (long long)(nr - 1) * Sg > klast) nr--;
+        if (nr == kRsR) {
+            for (int t = 0; t < T; t++) {
+                const float tap = gb[t];
+#pragma unroll
+                for (int r = 0; r < kRsR; r++) rs_mac(acc[r], xs[i0 + r * step + t], tap);
+            }
+        } else {
+            for (int t = 0; t < T; t++) {
+                const float tap = gb[t];
+#pragma unroll
+                for (int r = 0; r < kRsR; r++)
+                    if (r < nr) rs_mac(acc[r], xs[i0 + r * step + t], tap);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRsR; r++)
+            if (r < nr) out[k0 + (long long)r * Sg] = acc[r];
     }
 }
 
@@ -115,20 +137,22 @@ int32_t b2s_resamp_exec(b2s_resamp *r, const void *d_in, size_t n_in, void *d_ou
     if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_resamp_exec: NULL buffer");
     DeviceGuard g(ctx->device);
     const size_t isz = kind_in_bytes(r->kind);
-    const int span_max = (int)(((size_t)kRsTK * M) / L + T + 2);
+    const int G = (int)ceil_div((size_t)kRsThreads, L);                      // S = L*G >= 256 outputs per slab
+    const size_t tile_out = (size_t)kRsR * L * G;
+    const int span_max = (int)((tile_out * M) / L + T + 2);
     const size_t taps_bytes = L * r->pitch * sizeof(float);
     const size_t xs_bytes = round_up((size_t)span_max * isz, 16);
-    const bool taps_smem = xs_bytes + taps_bytes <= 96 * 1024;
+    const bool taps_smem = xs_bytes + taps_bytes <= 160 * 1024;
     const size_t smem = xs_bytes + (taps_smem ? taps_bytes : 0);
     if (xs_bytes > 200 * 1024) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_resamp_exec: decimation too large for one tile");
-    const unsigned grid = (unsigned)ceil_div(p, (size_t)kRsTK);
+    const unsigned grid = (unsigned)ceil_div(p, tile_out);
 #define RS_LAUNCH(S, TS)                                                                                     \
     do {                                                                                                     \
         auto kern = resamp_kernel<S, TS>;                                                                    \
         if (smem > 48 * 1024)                                                                                \
             B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, kRsThreads, smem, ctx->stream>>>((const S *)d_in, (S *)d_out, r->d_banks, (int)L, (int)M, \
-                                                      (int)T, r->pitch, (long long)p, (int)(xs_bytes / isz));  \
+                                                      (int)T, r->pitch, (long long)p, G, (int)(xs_bytes / isz)); \
     } while (0)
     if (r->kind == B2S_F32_F32) { if (taps_smem) RS_LAUNCH(float, true); else RS_LAUNCH(float, false); }
     else { if (taps_smem) RS_LAUNCH(float2, true); else RS_LAUNCH(float2, false); }

@@ -165,6 +165,21 @@ int32_t b2s_apply_reset(b2s_apply *a); /* closure state back to its initial valu
 int32_t b2s_apply_exec(b2s_apply *a, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
                        size_t *consumed, size_t *produced);
 
+/* ---- Rotator + XlatingFir helper (≙ futuredsp::Rotator, crates/futuredsp/src/rotator.rs:13-48;
+ * XlatingFir = DecimatingFirFilter with band-pass Complex<f32> taps + Rotator at the output rate,
+ * src/blocks/xlating_fir.rs:72-126 -- build the FIR with b2s_fir_plan(B2S_C32_C32, bpf, n, decim)).
+ * The rotator keeps its phase across calls exactly like the reference object. */
+typedef struct b2s_rotator b2s_rotator;
+int32_t b2s_rotator_create(b2s_ctx *ctx, float phase_incr, b2s_rotator **out);
+void    b2s_rotator_destroy(b2s_rotator *r);
+int32_t b2s_rotator_reset(b2s_rotator *r);
+/* ≙ Rotator::rotate (:32-47); d_in == d_out is rotate_inplace (:24-29). n = min(n_in, n_out_cap). */
+int32_t b2s_rotator_exec(b2s_rotator *r, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                         size_t *processed, int32_t *status);
+/* xlating_fir.rs:80-86 and :97-99: band-pass taps (2*ntaps floats) and the rotator's phase increment */
+int32_t b2s_xlating_taps(const float *taps, size_t ntaps, float offset, float sample_rate, size_t decimation,
+                         float *bpf_interleaved, float *rotator_phase_incr);
+
 /* ---- device-resident buffer ring (≙ buffer/vulkan/{h2d,d2h}.rs + circuit.rs + slab.rs history)
  * n_slots buffers of `halo_items + chunk_items` items each stay in HBM; ownership of a slot
  * moves source-edge -> GPU block(s) -> sink-edge -> back (circuit), exactly like

@@ -98,6 +98,12 @@ def _declare(L):
     L.orc_pfbarb_work.restype = None
     L.orc_pfbarb_work.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_size_t, _szp, _szp,
                                   C.POINTER(C.c_int)]
+    L.orc_rotator_incr.restype = None
+    L.orc_rotator_incr.argtypes = [C.c_float, _f32p]
+    L.orc_rotator_rotate.restype = None
+    L.orc_rotator_rotate.argtypes = [_f32p, C.c_size_t, _f32p, _f32p, _f32p]
+    L.orc_xlating_taps.restype = None
+    L.orc_xlating_taps.argtypes = [_f32p, C.c_size_t, C.c_float, C.c_float, _f32p]
     L.orc_max_threads.restype = C.c_int
     for name in ("orc_fir_c32_f32_mt", "orc_fir_c32_f32_fast_mt"):
         f = getattr(L, name)
@@ -300,6 +306,41 @@ class PfbArb:
             if c == 0 and p == 0 and not ca:
                 break
         return np.concatenate(outs) if outs else np.zeros(0, np.complex64)
+
+
+class Rotator:
+    """futuredsp::Rotator (crates/futuredsp/src/rotator.rs:13-48)."""
+
+    def __init__(self, phase_incr):
+        self.incr = np.zeros(2, np.float32)
+        lib().orc_rotator_incr(float(np.float32(phase_incr)), _p32(self.incr))
+        self.phase = np.array([1.0, 0.0], np.float32)
+
+    def rotate(self, x):
+        xi = _as(x, np.complex64)
+        out = np.zeros(xi.size, np.complex64)
+        lib().orc_rotator_rotate(_p32(xi.view(np.float32)), xi.size, _p32(out.view(np.float32)),
+                                 _p32(self.incr), _p32(self.phase))
+        return out
+
+
+def xlating_taps(taps, offset, sample_rate):
+    """Band-pass taps of XlatingFir (src/blocks/xlating_fir.rs:80-86)."""
+    t = _as(taps, np.float32)
+    out = np.zeros(t.size, np.complex64)
+    lib().orc_xlating_taps(_p32(t), t.size, float(np.float32(offset)), float(np.float32(sample_rate)),
+                           _p32(out.view(np.float32)))
+    return out
+
+
+def xlating_fir(taps, decimation, offset, sample_rate, x, chunks=None):
+    """XlatingFir::work over a stream (src/blocks/xlating_fir.rs:105-126): decimating FIR with the
+    band-pass taps, then the rotator at the output rate.  Returns the whole output."""
+    bpf = xlating_taps(taps, offset, sample_rate)
+    rot = Rotator(np.float32(-6.28318530717958647692) * np.float32(offset) * np.float32(decimation)
+                  / np.float32(sample_rate))
+    _, _, _, y = decim_fir(bpf, decimation, x, np.asarray(x).size)
+    return rot.rotate(y)
 
 
 def max_threads():

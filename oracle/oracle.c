@@ -583,3 +583,39 @@ void orc_fir_c32_f32_mt(const float *taps, size_t ntaps, const float *in, size_t
     }
     (void)threads;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Rotator -- crates/futuredsp/src/rotator.rs:13-48 ("next" row).
+ *   new(phase_incr): incr = Complex32::from_polar(1.0, phase_incr) = (cos, sin) in f32; phase = (1, 0)
+ *   per sample: phase *= incr; out = in * phase   (num_complex Mul, separate roundings)
+ * state: phase (2 floats, in/out).  "Parity unpinned": no reference test pins a Rotator value.
+ * ---------------------------------------------------------------------------------------- */
+void orc_rotator_incr(float phase_incr, float *incr) {
+    incr[0] = 1.0f * cosf(phase_incr);         /* from_polar(r, theta) = (r*cos(theta), r*sin(theta)) */
+    incr[1] = 1.0f * sinf(phase_incr);
+}
+
+void orc_rotator_rotate(const float *in, size_t n, float *out, const float *incr, float *phase) {
+    float pr = phase[0], pi = phase[1];
+    const float ir = incr[0], ii = incr[1];
+    for (size_t j = 0; j < n; j++) {
+        const float nr = pr * ir - pi * ii;    /* phase *= phase_incr */
+        const float ni = pr * ii + pi * ir;
+        pr = nr; pi = ni;
+        const float xr = in[2 * j], xi = in[2 * j + 1];
+        out[2 * j] = xr * pr - xi * pi;        /* *v *= phase */
+        out[2 * j + 1] = xr * pi + xi * pr;
+    }
+    phase[0] = pr; phase[1] = pi;
+}
+
+/* XlatingFir band-pass taps -- src/blocks/xlating_fir.rs:80-86:
+ *   bpf[i] = Complex32::from_polar(1.0, i as f32 * TAU * offset / sample_rate) * tap[i] */
+void orc_xlating_taps(const float *taps, size_t ntaps, float offset, float sample_rate, float *bpf) {
+    const float TAU = 6.28318530717958647692f;
+    for (size_t i = 0; i < ntaps; i++) {
+        const float th = (float)i * TAU * offset / sample_rate;
+        bpf[2 * i] = (1.0f * cosf(th)) * taps[i];
+        bpf[2 * i + 1] = (1.0f * sinf(th)) * taps[i];
+    }
+}

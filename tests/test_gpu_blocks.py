@@ -145,9 +145,29 @@ def test_fft_roundtrip_and_parseval_full_size(fb):
 def test_fft_unsupported_sizes_fail_loudly(fb):
     from futuresdr_b200.blocks import Fft
     with pytest.raises(fb.B200SdrError):
-        Fft(1000)
+        Fft(10000)                      # non-power-of-two beyond the Bluestein limit (8192)
     with pytest.raises(fb.B200SdrError):
         Fft(32768)
+    with pytest.raises(fb.B200SdrError):
+        Fft(1)
+
+
+@pytest.mark.parametrize("n", [3, 5, 6, 7, 12, 100, 1000, 1536, 4095, 5000, 8191])
+def test_fft_arbitrary_sizes_bluestein(fb, rng, n):
+    """rustfft plans any length; non-powers-of-two run the fused Bluestein kernel."""
+    import torch
+    from futuresdr_b200.blocks import Fft, FftDirection
+    nfft = 11 if n <= 1536 else 3
+    x = _noise(rng, n * nfft + min(2, n - 1))
+    for inverse, shift, norm in ((False, False, None), (False, True, None), (True, True, 1.0 / n), (True, False, None)):
+        fft = Fft.with_options(n, FftDirection.Inverse if inverse else FftDirection.Forward, shift, norm)
+        out = torch.zeros(x.size, dtype=torch.complex64, device="cuda")
+        m = fft.transform(_dev(x), out)
+        torch.cuda.synchronize()
+        m0, ref = orc.fft_block(x, n, inverse=inverse, fft_shift=shift, normalize=norm)
+        assert m == m0 == n * nfft
+        got, r = out[:m].cpu().numpy().reshape(nfft, n), ref.reshape(nfft, n)
+        assert np.all(np.max(np.abs(got - r), axis=1) <= 1e-5 * np.max(np.abs(r), axis=1)), (n, inverse, shift)
 
 
 # ---------------------------------------------------------------------------------------------
