@@ -369,6 +369,53 @@ class XlatingFir(Block):
             io.finished = True
 
 
+class PfbChannelizer(Block):
+    """blocks::PfbChannelizer (src/blocks/pfb/channelizer.rs:72-223): one input, N output streams.
+    The N output ports share one channel-major device buffer ``outputs`` of shape [N, capacity];
+    ``produced`` items have been written to every row."""
+
+    def __init__(self, num_channels: int, taps, oversample_rate: float = 1.0, ctx: Optional[Context] = None):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        # validate input (channelizer.rs:92-104: the reference asserts)
+        assert num_channels > 2, "PfbChannelizer: number of channels must be at least 2"
+        assert taps.size >= num_channels, "PfbChannelizer: prototype filter length must be at least num_channels"
+        assert oversample_rate != 0.0 and (num_channels % oversample_rate) == 0.0, \
+            "pfb_channelizer: oversample rate must be N/i for i in [1, N]"
+        self.ctx = ctx or default_context()
+        self.num_channels = int(num_channels)
+        self._h = C.c_void_p()
+        check(lib.b2s_chan_plan_c32(self.ctx.handle, self.num_channels, taps.ctypes.data_as(C.POINTER(C.c_float)),
+                                    taps.size, float(oversample_rate), C.byref(self._h)), self.ctx.handle)
+        self.decimation_factor = int(lib.b2s_chan_decimation(self._h))
+        self.input = Reader(np.complex64)
+        self.outputs = torch.zeros(self.num_channels, 0, dtype=torch.complex64, device="cuda")
+        self.produced = 0
+
+    def reserve_outputs(self, n: int):
+        self.outputs = torch.zeros(self.num_channels, n, dtype=torch.complex64, device="cuda")
+        self.produced = 0
+
+    def work(self, io: WorkIo):
+        i = self.input.slice()
+        cap = self.outputs.shape[1] - self.produced
+        c, p, ca = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
+        out_ptr = self.outputs.data_ptr() + 8 * self.produced
+        check(lib.b2s_chan_exec(self._h, C.c_void_p(i.data_ptr()), i.numel(), C.c_void_p(out_ptr),
+                                self.outputs.shape[1], cap, C.byref(c), C.byref(p), C.byref(ca)), self.ctx.handle)
+        n_in = i.numel()
+        self.input.consume(c.value)
+        self.produced += p.value
+        if ca.value:
+            io.call_again = True
+        elif n_in - c.value < self.decimation_factor and self.input.finished():      # :214-218
+            io.finished = True
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_chan_destroy(self._h)
+            self._h = None
+
+
 class Mocker:
     """runtime::mocker::Mocker (src/runtime/mocker.rs:33-190): run ONE block without a scheduler."""
 

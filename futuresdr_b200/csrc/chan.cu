@@ -1,0 +1,251 @@
+// chan.cu -- polyphase channelizer (src/blocks/pfb/channelizer.rs:88-223) on the device:
+// SURVEY.md §8f row 2, a pure composition of the FIR-bank and FFT pieces of the hot path.
+//
+// Reference semantics restated: every consumed sample is pushed into window `base_index`, which
+// then decrements modulo N -- so window w holds the stream decimated by N at phase (base0 - w);
+// after each group of D = N / oversample_rate pushes, arm i (taps[i::N]) filters window
+// (base_index + i + 1) % N into fft_buf[that window], an un-normalised inverse FFT over the N
+// buffers de-spins, and element ch goes to output stream ch.
+//   * start-up: windows fill through WindowBuffer::push, which scatters the first T samples of a
+//     window (window_buffer.rs:24-32), and the call in which the last window fills returns
+//     WITHOUT consuming (channelizer.rs:170-180), so those samples are pushed a second time.
+//     Both are reproduced: a one-thread kernel replays the pushes on the data, the host mirrors
+//     the bookkeeping (it is data-independent).
+//   * steady state is closed-form: one thread per (output vector o, window b) gathers the T newest
+//     samples of its phase (history buffer + this call's input) and dots them with its arm; the
+//     N-point inverse FFT is the batched FFT kernel of fft.cu (any N: radix or Bluestein), a
+//     transposing store writes channel-major output streams.
+#include <cmath>
+
+#include "common.cuh"
+
+struct b2s_chan {
+    b2s_ctx *ctx = nullptr;
+    size_t N = 0, D = 0, T = 0;
+    float *d_arms = nullptr;        // [N][T]: arm_i[j] = taps[i + j*N] (utilities.rs order; newest sample <-> j = 0)
+    float2 *d_circ = nullptr;       // [N][2T] circular windows (used while filling)
+    float2 *d_hist = nullptr;       // [N][T] windows in time order once filled
+    int *d_wstate = nullptr;        // [2N]: start_idx[N], missing[N]
+    std::vector<int> start_idx, missing;   // host mirror of the WindowBuffer bookkeeping
+    size_t base_index = 0;
+    bool all_filled = false;
+    b2s_fft *ifft = nullptr;
+    float2 *d_tmp = nullptr;        // 2 * tmp_items
+    size_t tmp_items = 0;
+};
+
+namespace {
+
+__global__ void chan_fill_kernel(const float2 *__restrict__ in, float2 *circ, int *wstate, int N, int T,
+                                 int base_index, int count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int *start = wstate, *missing = wstate + N;
+    for (int c = 0; c < count; c++) {
+        const int w = base_index;
+        int idx = (start[w] - missing[w]) % T;
+        if (idx < 0) idx += T;
+        float2 *cw = circ + (size_t)w * 2 * T;
+        cw[idx] = in[c]; cw[idx + T] = in[c];
+        if (missing[w] > 0) missing[w]--;
+        start[w] = (start[w] + 1) % T;
+        base_index = base_index == 0 ? N - 1 : base_index - 1;
+    }
+}
+
+__global__ void chan_hist_from_circ(const float2 *__restrict__ circ, const int *__restrict__ wstate, float2 *hist,
+                                    int N, int T) {
+    const int w = blockIdx.x;
+    const int s = wstate[w];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) hist[(size_t)w * T + t] = circ[(size_t)w * 2 * T + s + t];
+}
+
+// j-th newest sample of window b when E = (o+1)*D samples of this call have been pushed
+__device__ __forceinline__ float2 chan_sample(const float2 *__restrict__ in, const float2 *__restrict__ hist,
+                                              int T, int N, long long c_new, int m, int b, int j) {
+    if (j < m) return __ldg(in + (c_new - (long long)j * N));
+    return hist[(size_t)b * T + (T - 1 - (j - m))];
+}
+
+__global__ void chan_bank_kernel(const float2 *__restrict__ in, const float2 *__restrict__ hist,
+                                 const float *__restrict__ arms, float2 *__restrict__ fftbuf, int N, int D, int T,
+                                 int base0, long long nprod) {
+    const long long total = nprod * N;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const long long o = g / N;
+        const int b = (int)(g % N);                                    // window / fft_buf index
+        const long long E = (o + 1) * D;                               // pushes done when output o is formed
+        const int r = ((base0 - b) % N + N) % N;                        // this window receives c == r (mod N)
+        long long c_new = -1; int m = 0;
+        if (E - 1 >= r) { c_new = r + ((E - 1 - r) / N) * N; m = (int)((c_new - r) / N) + 1; }
+        const int base_after = (int)(((base0 - E) % N + N) % N);
+        const int i = ((b - base_after - 1) % N + N) % N;               // arm: b = (base_after + i + 1) % N
+        const float *a = arms + (size_t)i * T;
+        float re = 0.f, im = 0.f;
+        // reference order: t = 0 (oldest) .. T-1 with tap arm[T-1-t]  <=>  j = T-1 .. 0 with tap arm[j]
+        for (int j = T - 1; j >= 0; j--) {
+            const float2 x = chan_sample(in, hist, T, N, c_new, m, b, j);
+            const float tap = a[j];
+            re = fmaf(x.x, tap, re); im = fmaf(x.y, tap, im);
+        }
+        fftbuf[g] = make_float2(re, im);
+    }
+}
+
+__global__ void chan_hist_update(float2 *hist, const float2 *__restrict__ in, int N, int T, int base0, long long npush) {
+    extern __shared__ float2 tmp[];
+    const int b = blockIdx.x;
+    const int r = ((base0 - b) % N + N) % N;
+    long long c_new = -1; int m = 0;
+    if (npush - 1 >= r) { c_new = r + ((npush - 1 - r) / N) * N; m = (int)((c_new - r) / N) + 1; }
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int j = T - 1 - t;                                       // new hist[t] = j-th newest
+        tmp[t] = (j < m) ? in[c_new - (long long)j * N] : hist[(size_t)b * T + (T - 1 - (j - m))];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) hist[(size_t)b * T + t] = tmp[t];
+}
+
+// out[ch * stride + o] = spec[o * N + ch]
+__global__ void chan_transpose_kernel(const float2 *__restrict__ spec, float2 *__restrict__ out, int N, long long nprod,
+                                      long long stride) {
+    __shared__ float2 tile[32][33];
+    const long long o0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long o = o0 + i; const int ch = c0 + threadIdx.x;
+        if (o < nprod && ch < N) tile[i][threadIdx.x] = spec[o * N + ch];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int ch = c0 + i; const long long o = o0 + threadIdx.x;
+        if (o < nprod && ch < N) out[(long long)ch * stride + o] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void b2s_chan_destroy(b2s_chan *c);
+
+int32_t b2s_chan_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps, size_t ntaps, float oversample_rate,
+                          b2s_chan **out) {
+    if (!ctx || !out || !taps) return b2s_fail(ctx, B2S_EINVAL, "b2s_chan_plan_c32: NULL argument");
+    *out = nullptr;
+    // the reference asserts these (channelizer.rs:92-104)
+    if (num_channels <= 2) return b2s_fail(ctx, B2S_EINVAL, "PfbChannelizer: number of channels must be at least 2");
+    if (ntaps < num_channels) return b2s_fail(ctx, B2S_EINVAL, "PfbChannelizer: prototype filter length must be at least num_channels");
+    if (oversample_rate == 0.f || std::fmod((float)num_channels, oversample_rate) != 0.f)
+        return b2s_fail(ctx, B2S_EINVAL, "pfb_channelizer: oversample rate must be N/i for i in [1, N]");
+    DeviceGuard g(ctx->device);
+    b2s_chan *c = new b2s_chan();
+    c->ctx = ctx; c->N = num_channels;
+    c->D = (size_t)((float)num_channels / oversample_rate);                      // channelizer.rs:106
+    const size_t N = c->N, T = (size_t)std::ceil((float)ntaps / (float)N);       // utilities.rs:9
+    c->T = T;
+    std::vector<float> arms(N * T, 0.0f);
+    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) arms[i * T + j++] = taps[idx]; }
+    c->start_idx.assign(N, 0); c->missing.assign(N, (int)T);
+    c->base_index = N - 1;
+    int32_t rc = b2s_fft_plan_c32(ctx, N, 1, 0, 0, 1.0f, &c->ifft);              // plan_fft(n, Inverse) (:114)
+    if (rc != B2S_OK) { delete c; return rc; }
+    if (cudaMalloc((void **)&c->d_arms, arms.size() * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_circ, N * 2 * T * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_hist, N * T * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_wstate, 2 * N * sizeof(int)) != cudaSuccess) {
+        b2s_chan_destroy(c);
+        return b2s_fail(ctx, B2S_ENOMEM, "channelizer buffers");
+    }
+    std::vector<int> ws(2 * N);
+    for (size_t i = 0; i < N; i++) { ws[i] = 0; ws[N + i] = (int)T; }
+    B2S_CUDA(ctx, cudaMemcpyAsync(c->d_arms, arms.data(), arms.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    B2S_CUDA(ctx, cudaMemcpyAsync(c->d_wstate, ws.data(), ws.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    B2S_CUDA(ctx, cudaMemsetAsync(c->d_circ, 0, N * 2 * T * sizeof(float2), ctx->stream));
+    B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = c;
+    return B2S_OK;
+}
+
+void b2s_chan_destroy(b2s_chan *c) {
+    if (!c) return;
+    DeviceGuard g(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->ifft) b2s_fft_destroy(c->ifft);
+    if (c->d_arms) cudaFree(c->d_arms);
+    if (c->d_circ) cudaFree(c->d_circ);
+    if (c->d_hist) cudaFree(c->d_hist);
+    if (c->d_wstate) cudaFree(c->d_wstate);
+    if (c->d_tmp) cudaFree(c->d_tmp);
+    delete c;
+}
+
+size_t b2s_chan_decimation(const b2s_chan *c) { return c ? c->D : 0; }
+
+// One Kernel::work call (channelizer.rs:142-223).  d_out is channel-major: stream ch starts at
+// d_out + ch * out_stride items; n_out_cap = the smallest free space over the N output slices.
+int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, size_t out_stride, size_t n_out_cap,
+                      size_t *consumed, size_t *produced_per_channel, int32_t *call_again) {
+    if (!c || !consumed || !produced_per_channel || !call_again)
+        return b2s_fail(c ? c->ctx : nullptr, B2S_EINVAL, "b2s_chan_exec: NULL argument");
+    b2s_ctx *ctx = c->ctx;
+    *consumed = 0; *produced_per_channel = 0; *call_again = 0;
+    DeviceGuard g(ctx->device);
+    const int N = (int)c->N, T = (int)c->T, D = (int)c->D;
+    const float2 *in = (const float2 *)d_in;
+    if (!c->all_filled) {
+        // host mirror of the push bookkeeping decides how many samples this call pushes
+        size_t cnt = 0;
+        size_t base = c->base_index;
+        auto all_filled = [&]() { for (int m : c->missing) if (m) return false; return true; };
+        while (!all_filled() && cnt < n_in) {
+            if (c->missing[base] > 0) c->missing[base]--;
+            c->start_idx[base] = (c->start_idx[base] + 1) % T;
+            base = base == 0 ? (size_t)N - 1 : base - 1;
+            cnt++;
+        }
+        if (cnt) {
+            if (!d_in) return b2s_fail(ctx, B2S_EINVAL, "b2s_chan_exec: NULL buffer");
+            chan_fill_kernel<<<1, 32, 0, ctx->stream>>>(in, c->d_circ, c->d_wstate, N, T, (int)c->base_index, (int)cnt);
+            B2S_CHECK_LAUNCH(ctx);
+        }
+        c->base_index = base;
+        if (!all_filled()) { *consumed = cnt; return B2S_OK; }               // input exhausted first (:165-170)
+        c->all_filled = true;
+        chan_hist_from_circ<<<N, 64, 0, ctx->stream>>>(c->d_circ, c->d_wstate, c->d_hist, N, T);
+        B2S_CHECK_LAUNCH(ctx);
+        if (n_in >= (size_t)D) *call_again = 1;                                // :176-177; NB nothing is consumed here
+        return B2S_OK;
+    }
+    size_t nprod = n_in / D;
+    if (nprod > n_out_cap) nprod = n_out_cap;                                  // :155-158
+    if (nprod == 0) return B2S_OK;
+    if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_chan_exec: NULL buffer");
+    const size_t items = nprod * N;
+    if (c->tmp_items < items) {
+        B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (c->d_tmp) cudaFree(c->d_tmp);
+        c->tmp_items = items * 5 / 4 + 1024;
+        cudaError_t e = cudaMalloc((void **)&c->d_tmp, 2 * c->tmp_items * sizeof(float2));
+        if (e != cudaSuccess) { c->d_tmp = nullptr; c->tmp_items = 0; cudaGetLastError(); return b2s_fail(ctx, B2S_ENOMEM, "channelizer workspace"); }
+    }
+    float2 *bank = c->d_tmp, *spec = c->d_tmp + c->tmp_items;
+    const int th = 256;
+    const unsigned grid = (unsigned)std::min<size_t>(ceil_div(items, (size_t)th), (size_t)ctx->sm_count * 32);
+    chan_bank_kernel<<<grid, th, 0, ctx->stream>>>(in, c->d_hist, c->d_arms, bank, N, D, T, (int)c->base_index, (long long)nprod);
+    B2S_CHECK_LAUNCH(ctx);
+    size_t fc = 0, fp = 0;
+    int32_t rc = b2s_fft_exec(c->ifft, bank, items, spec, items, &fc, &fp);
+    if (rc != B2S_OK) return rc;
+    dim3 tg((unsigned)ceil_div(nprod, (size_t)32), (unsigned)ceil_div((size_t)N, (size_t)32));
+    chan_transpose_kernel<<<tg, dim3(32, 8), 0, ctx->stream>>>(spec, (float2 *)d_out, N, (long long)nprod, (long long)out_stride);
+    B2S_CHECK_LAUNCH(ctx);
+    const long long npush = (long long)nprod * D;
+    chan_hist_update<<<N, 64, T * sizeof(float2), ctx->stream>>>(c->d_hist, in, N, T, (int)c->base_index, npush);
+    B2S_CHECK_LAUNCH(ctx);
+    c->base_index = (size_t)((((long long)c->base_index - npush) % N + N) % N);
+    *consumed = (size_t)npush; *produced_per_channel = nprod;
+    return B2S_OK;
+}
+
+}  // extern "C"

@@ -180,6 +180,18 @@ int32_t b2s_rotator_exec(b2s_rotator *r, const void *d_in, size_t n_in, void *d_
 int32_t b2s_xlating_taps(const float *taps, size_t ntaps, float offset, float sample_rate, size_t decimation,
                          float *bpf_interleaved, float *rotator_phase_incr);
 
+/* ---- PfbChannelizer (≙ src/blocks/pfb/channelizer.rs:88-223): polyphase FIR bank +
+ * N-point inverse FFT per output vector.  Stateful like the block: one exec == one Kernel::work
+ * call (window fill first; note the reference does not consume on the call that completes the fill).
+ * d_out is channel-major: output stream ch starts at d_out + ch * out_stride items. */
+typedef struct b2s_chan b2s_chan;
+int32_t b2s_chan_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps, size_t ntaps, float oversample_rate,
+                          b2s_chan **out);
+void    b2s_chan_destroy(b2s_chan *c);
+size_t  b2s_chan_decimation(const b2s_chan *c);
+int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, size_t out_stride, size_t n_out_cap,
+                      size_t *consumed, size_t *produced_per_channel, int32_t *call_again);
+
 /* ---- device-resident buffer ring (≙ buffer/vulkan/{h2d,d2h}.rs + circuit.rs + slab.rs history)
  * n_slots buffers of `halo_items + chunk_items` items each stay in HBM; ownership of a slot
  * moves source-edge -> GPU block(s) -> sink-edge -> back (circuit), exactly like

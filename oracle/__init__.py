@@ -324,6 +324,52 @@ class Rotator:
         return out
 
 
+class PfbChannelizer:
+    """PfbChannelizer state machine (src/blocks/pfb/channelizer.rs:88-223)."""
+
+    def __init__(self, num_channels, taps, oversample_rate=1.0):
+        taps = _as(taps, np.float32)
+        assert num_channels > 2 and taps.size >= num_channels
+        assert oversample_rate != 0 and (num_channels % oversample_rate) == 0
+        L = lib()
+        L.orc_chan_new.restype = C.c_void_p
+        L.orc_chan_new.argtypes = [C.c_size_t, _f32p, C.c_size_t, C.c_float]
+        L.orc_chan_free.restype = None
+        L.orc_chan_free.argtypes = [C.c_void_p]
+        L.orc_chan_work.restype = None
+        L.orc_chan_work.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, _szp, _szp,
+                                    C.POINTER(C.c_int)]
+        self.N = num_channels
+        self.D = int(np.float32(num_channels) / np.float32(oversample_rate))
+        self._h = L.orc_chan_new(num_channels, _p32(taps), taps.size, float(oversample_rate))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_chan_free(self._h)
+            self._h = None
+
+    def work(self, x, out_cap):
+        """One Kernel::work call -> (consumed, produced_per_channel, call_again, out[N, produced])."""
+        xi = _as(x, np.complex64)
+        out = np.zeros((self.N, max(out_cap, 1)), np.complex64)
+        c, p, ca = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+        lib().orc_chan_work(self._h, _p32(xi.view(np.float32)), xi.size, _p32(out.view(np.float32).reshape(-1)),
+                            max(out_cap, 1), out_cap, C.byref(c), C.byref(p), C.byref(ca))
+        return c.value, p.value, bool(ca.value), out[:, : p.value].copy()
+
+    def run(self, x, out_cap_per_call=1 << 16):
+        """Mocker-style loop: call work() until nothing more can be consumed."""
+        xi = _as(x, np.complex64)
+        outs, pos = [], 0
+        for _ in range(1 << 20):
+            c, p, ca, o = self.work(xi[pos:], out_cap_per_call)
+            pos += c
+            outs.append(o)
+            if c == 0 and p == 0 and not ca:
+                break
+        return np.concatenate(outs, axis=1)
+
+
 def xlating_taps(taps, offset, sample_rate):
     """Band-pass taps of XlatingFir (src/blocks/xlating_fir.rs:80-86)."""
     t = _as(taps, np.float32)

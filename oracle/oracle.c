@@ -619,3 +619,91 @@ void orc_xlating_taps(const float *taps, size_t ntaps, float offset, float sampl
         bpf[2 * i + 1] = (1.0f * sinf(th)) * taps[i];
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * PfbChannelizer -- src/blocks/pfb/channelizer.rs:88-223 ("next" row), with
+ * partition_filter_taps (pfb/utilities.rs:5-25) and WindowBuffer (pfb/window_buffer.rs:13-44).
+ * Streaming object driven call-by-call like Kernel::work.  Outputs are written channel-major:
+ * out[ch * out_stride + k].  The IFFT (rustfft, un-normalised inverse) is evaluated in f64.
+ * "Parity unpinned": no reference test constructs this block.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    size_t N, D, T;              /* channels, decimation_factor, taps per arm */
+    float *arms;                 /* [N][T] utilities.rs order */
+    float *circ;                 /* [N][2T] complex */
+    size_t *start_idx, *missing; /* per window */
+    size_t base_index;
+    int all_filled;
+} orc_chan;
+
+orc_chan *orc_chan_new(size_t num_channels, const float *taps, size_t ntaps, float oversample_rate) {
+    orc_chan *s = (orc_chan *)calloc(1, sizeof(orc_chan));
+    size_t N = num_channels;
+    s->N = N; s->D = (size_t)((float)N / oversample_rate);                    /* channelizer.rs:106 */
+    size_t T = (size_t)ceilf((float)ntaps / (float)N);
+    s->T = T;
+    s->arms = (float *)calloc(N * T, sizeof(float));
+    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) s->arms[i * T + j++] = taps[idx]; }
+    s->circ = (float *)calloc(N * 4 * T, sizeof(float));
+    s->start_idx = (size_t *)calloc(N, sizeof(size_t));
+    s->missing = (size_t *)calloc(N, sizeof(size_t));
+    for (size_t i = 0; i < N; i++) s->missing[i] = T;
+    s->base_index = N - 1; s->all_filled = 0;
+    return s;
+}
+void orc_chan_free(orc_chan *s) { if (s) { free(s->arms); free(s->circ); free(s->start_idx); free(s->missing); free(s); } }
+
+static void chan_push(orc_chan *s, size_t w, float re, float im) {              /* window_buffer.rs:24-32 */
+    long L = (long)s->T;
+    long idx = ((long)s->start_idx[w] - (long)s->missing[w]) % L; if (idx < 0) idx += L;
+    float *c = s->circ + w * 4 * s->T;
+    c[2 * idx] = re; c[2 * idx + 1] = im; c[2 * (idx + L)] = re; c[2 * (idx + L) + 1] = im;
+    if (s->missing[w] > 0) s->missing[w]--;
+    s->start_idx[w] = (s->start_idx[w] + 1) % s->T;
+}
+static int chan_all_filled(const orc_chan *s) { for (size_t i = 0; i < s->N; i++) if (s->missing[i]) return 0; return 1; }
+static void chan_dec(orc_chan *s) { s->base_index = s->base_index == 0 ? s->N - 1 : s->base_index - 1; }
+
+/* one work() call; n_out_cap = min over channels of the output slice length.  Returns consumed and
+ * produced-per-channel; *call_again as io.call_again. */
+void orc_chan_work(orc_chan *s, const float *in, size_t n_in, float *out, size_t out_stride, size_t n_out_cap,
+                   size_t *consumed, size_t *produced, int *call_again) {
+    *consumed = 0; *produced = 0; *call_again = 0;
+    size_t nprod = n_in / s->D; if (nprod > n_out_cap) nprod = n_out_cap;       /* :155-158 */
+    if (!s->all_filled) {                                                      /* :160-181 */
+        size_t c = 0;
+        while (!chan_all_filled(s)) {
+            if (c == n_in) { *consumed = c; return; }
+            chan_push(s, s->base_index, in[2 * c], in[2 * c + 1]);
+            chan_dec(s); c++;
+        }
+        s->all_filled = 1;
+        if (n_in >= s->D) *call_again = 1;
+        /* NB: the reference returns WITHOUT consuming here (:176-180 never call input.consume), so the
+         * samples pushed during this call are presented again and pushed a second time. */
+        return;
+    }
+    size_t N = s->N, T = s->T;
+    double *br = (double *)malloc(4 * N * sizeof(double)), *bi = br + N, *yr = bi + N, *yi = yr + N;
+    for (size_t o = 0; o < nprod; o++) {
+        for (size_t j = 0; j < s->D; j++) {
+            chan_push(s, s->base_index, in[2 * (o * s->D + j)], in[2 * (o * s->D + j) + 1]);
+            chan_dec(s);
+        }
+        float *fb = (float *)malloc(2 * N * sizeof(float));
+        for (size_t i = 0; i < N; i++) {
+            size_t bidx = (s->base_index + i + 1) % N;                          /* :190 */
+            const float *win = s->circ + bidx * 4 * T + 2 * s->start_idx[bidx];
+            const float *a = s->arms + i * T;
+            float re = 0.0f, im = 0.0f;
+            for (size_t t = 0; t < T; t++) { float tap = a[T - 1 - t]; re = re + win[2 * t] * tap; im = im + win[2 * t + 1] * tap; }
+            fb[2 * bidx] = re; fb[2 * bidx + 1] = im;
+        }
+        for (size_t i = 0; i < N; i++) { br[i] = fb[2 * i]; bi[i] = fb[2 * i + 1]; }
+        dft_f64(br, bi, yr, yi, N, 1);                                          /* ifft.process (:201) */
+        for (size_t ch = 0; ch < N; ch++) { out[2 * (ch * out_stride + o)] = (float)yr[ch]; out[2 * (ch * out_stride + o) + 1] = (float)yi[ch]; }
+        free(fb);
+    }
+    free(br);
+    *consumed = nprod * s->D; *produced = nprod;
+}
