@@ -369,6 +369,38 @@ class XlatingFir(Block):
             io.finished = True
 
 
+class MovingAvg(Block):
+    """blocks::MovingAvg<WIDTH> (src/blocks/moving_avg.rs:24-116): exponential average per bin over
+    consecutive WIDTH-item chunks, one output chunk every ``history_size`` input chunks."""
+    in_dtype = np.float32
+    out_dtype = np.float32
+
+    def __init__(self, width: int, decay_factor: float, history_size: int, ctx: Optional[Context] = None):
+        assert 0.0 <= decay_factor <= 1.0, "decay_factor must be in [0, 1]"       # moving_avg.rs:58-61
+        self.ctx = ctx or default_context()
+        self.width = int(width)
+        self._h = C.c_void_p()
+        check(lib.b2s_mavg_create(self.ctx.handle, self.width, float(decay_factor), int(history_size),
+                                  C.byref(self._h)), self.ctx.handle)
+        self._ports()
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()
+        input_len = i.numel()
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        check(lib.b2s_mavg_exec(self._h, C.c_void_p(i.data_ptr()), input_len, C.c_void_p(o.data_ptr()), o.numel(),
+                                C.byref(c), C.byref(p)), self.ctx.handle)
+        if self.input.finished() and c.value // self.width == input_len // self.width:     # :106-108
+            io.finished = True
+        self.input.consume(c.value)
+        self.output.produce(p.value)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_mavg_destroy(self._h)
+            self._h = None
+
+
 class PfbChannelizer(Block):
     """blocks::PfbChannelizer (src/blocks/pfb/channelizer.rs:72-223): one input, N output streams.
     The N output ports share one channel-major device buffer ``outputs`` of shape [N, capacity];

@@ -42,14 +42,17 @@ template <typename S> __device__ __forceinline__ S zero_of();
 template <> __device__ __forceinline__ float zero_of<float>() { return 0.0f; }
 template <> __device__ __forceinline__ float2 zero_of<float2>() { return make_float2(0.f, 0.f); }
 
+// rq: phase-row index; XOR-ing it into the chunk swizzle keeps a row's own reads conflict-free
+// (a constant XOR permutes the 8 bank groups) and spreads the de-interleaving stores of the D
+// phases -- which hit the same column of D different rows -- over different bank groups.
 template <typename S, int R>
-__device__ __forceinline__ void load_segment(S (&dst)[R], const unsigned char *row, int seg) {
+__device__ __forceinline__ void load_segment(S (&dst)[R], const unsigned char *row, int seg, int rq) {
     constexpr int EPC = 16 / sizeof(S);   // items per 16-byte chunk
     constexpr int CPS = R / EPC;          // chunks per R-item segment
 #pragma unroll
     for (int j = 0; j < CPS; j++) {
         const int chunk = seg * CPS + j;
-        const float4 v = *reinterpret_cast<const float4 *>(row + swz(chunk) * 16);
+        const float4 v = *reinterpret_cast<const float4 *>(row + (swz(chunk) ^ rq) * 16);
         if constexpr (sizeof(S) == 8) {
             dst[2 * j] = *reinterpret_cast<const S *>(&v.x);
             dst[2 * j + 1] = *reinterpret_cast<const S *>(&v.z);
@@ -106,7 +109,7 @@ fir_direct_kernel(const S *__restrict__ in, S *__restrict__ out, const T *__rest
             const long long s = s0 + j;
             const S v = (s < n_in) ? in[s] : zero_of<S>();
             const int chunk = m / EPC, e = m % EPC;
-            *reinterpret_cast<S *>(xs + ((size_t)q * pitch + swz(chunk) * EPC + e) * sizeof(S)) = v;
+            *reinterpret_cast<S *>(xs + ((size_t)q * pitch + (swz(chunk) ^ (q & 7)) * EPC + e) * sizeof(S)) = v;
             q += dq; m += dm;
             if (q >= D) { q -= D; m += 1; }
         }
@@ -125,13 +128,13 @@ fir_direct_kernel(const S *__restrict__ in, S *__restrict__ out, const T *__rest
         S win[2 * R];
         {
             S first[R];
-            load_segment<S, R>(first, row, tid);
+            load_segment<S, R>(first, row, tid, q & 7);
 #pragma unroll
             for (int r = 0; r < R; r++) win[r] = first[r];
         }
         for (int c = 0; c < nchunk_taps; c++) {
             S nxt[R];
-            load_segment<S, R>(nxt, row, tid + c + 1);
+            load_segment<S, R>(nxt, row, tid + c + 1, q & 7);
 #pragma unroll
             for (int r = 0; r < R; r++) win[R + r] = nxt[r];
             T tp[R];

@@ -192,6 +192,14 @@ size_t  b2s_chan_decimation(const b2s_chan *c);
 int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, size_t out_stride, size_t n_out_cap,
                       size_t *consumed, size_t *produced_per_channel, int32_t *call_again);
 
+/* ---- MovingAvg<WIDTH> (≙ src/blocks/moving_avg.rs:24-116; SURVEY §8f-3, tail of the spectrum pipe
+ * Fft(shift) -> |x|^2 -> MovingAvg).  f32 items; state (avg[WIDTH], chunk counter) kept on the device. */
+typedef struct b2s_mavg b2s_mavg;
+int32_t b2s_mavg_create(b2s_ctx *ctx, size_t width, float decay_factor, size_t history_size, b2s_mavg **out);
+void    b2s_mavg_destroy(b2s_mavg *m);
+int32_t b2s_mavg_exec(b2s_mavg *m, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                      size_t *consumed, size_t *produced);
+
 /* ---- device-resident buffer ring (≙ buffer/vulkan/{h2d,d2h}.rs + circuit.rs + slab.rs history)
  * n_slots buffers of `halo_items + chunk_items` items each stay in HBM; ownership of a slot
  * moves source-edge -> GPU block(s) -> sink-edge -> back (circuit), exactly like

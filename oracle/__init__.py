@@ -370,6 +370,28 @@ class PfbChannelizer:
         return np.concatenate(outs, axis=1)
 
 
+class MovingAvg:
+    """MovingAvg<WIDTH> (src/blocks/moving_avg.rs:24-116)."""
+
+    def __init__(self, width, decay_factor, history_size):
+        assert 0.0 <= decay_factor <= 1.0, "decay_factor must be in [0, 1]"
+        self.width, self.decay, self.history = int(width), float(np.float32(decay_factor)), int(history_size)
+        self.avg = np.zeros(self.width, np.float32)
+        self.i = C.c_size_t(0)
+        L = lib()
+        L.orc_mavg_work.restype = None
+        L.orc_mavg_work.argtypes = [_f32p, _szp, C.c_size_t, C.c_float, C.c_size_t, _f32p, C.c_size_t, _f32p,
+                                    C.c_size_t, _szp, _szp]
+
+    def work(self, x, out_cap):
+        xi = _as(x, np.float32)
+        out = np.zeros(max(out_cap, 1), np.float32)
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        lib().orc_mavg_work(_p32(self.avg), C.byref(self.i), self.width, self.decay, self.history, _p32(xi),
+                            xi.size, _p32(out), out_cap, C.byref(c), C.byref(p))
+        return c.value, p.value, out[: p.value].copy()
+
+
 def xlating_taps(taps, offset, sample_rate):
     """Band-pass taps of XlatingFir (src/blocks/xlating_fir.rs:80-86)."""
     t = _as(taps, np.float32)

@@ -707,3 +707,26 @@ void orc_chan_work(orc_chan *s, const float *in, size_t n_in, float *out, size_t
     free(br);
     *consumed = nprod * s->D; *produced = nprod;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * MovingAvg<WIDTH> -- src/blocks/moving_avg.rs:72-115 (spectrum pipe tail).
+ * state: avg[width] and the chunk counter *i (in/out).  Returns consumed/produced in items.
+ * ---------------------------------------------------------------------------------------- */
+void orc_mavg_work(float *avg, size_t *i, size_t width, float decay, size_t history, const float *in,
+                   size_t n_in, float *out, size_t n_out_cap, size_t *consumed, size_t *produced) {
+    size_t c = 0, p = 0;
+    while ((c + 1) * width <= n_in && (p + 1) * width <= n_out_cap) {
+        for (size_t b = 0; b < width; b++) {
+            float t = in[c * width + b];
+            if (isfinite(t)) avg[b] = (1.0f - decay) * avg[b] + decay * t;
+            else avg[b] *= 1.0f - decay;
+        }
+        *i += 1;
+        if (*i == history) {
+            memcpy(out + p * width, avg, width * sizeof(float));
+            *i = 0; p++;
+        }
+        c++;
+    }
+    *consumed = c * width; *produced = p * width;
+}

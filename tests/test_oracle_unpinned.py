@@ -141,3 +141,43 @@ def test_pfbarb_window_fill_quirk_is_reproduced():
     y = orc.PfbArb(1.0, taps, 4).run(x)
     ref = PyPfbArb(1.0, taps, 4).run(x)
     assert np.array_equal(y, ref) and y.size > 0
+
+
+def test_rotator_oracle_short_run_matches_closed_form(rng):
+    # over a short run the f32 recurrence is still within ~n*eps of exp(i*n*incr)
+    x = (rng.standard_normal(200) + 1j * rng.standard_normal(200)).astype(np.complex64)
+    r = orc.Rotator(0.3)
+    y = r.rotate(x)
+    ref = x.astype(np.complex128) * np.exp(1j * 0.3 * np.arange(1, 201))
+    assert np.max(np.abs(y - ref)) < 1e-4
+    # state continues across calls
+    r2 = orc.Rotator(0.3)
+    assert np.array_equal(np.concatenate([r2.rotate(x[:77]), r2.rotate(x[77:])]), y)
+
+
+def test_xlating_taps_oracle():
+    taps = np.array([1.0, 2.0, 3.0], np.float32)
+    bpf = orc.xlating_taps(taps, 1000.0, 8000.0)
+    want = taps * np.exp(1j * 2 * np.pi * 1000.0 / 8000.0 * np.arange(3))
+    assert np.allclose(bpf, want, atol=1e-6)
+
+
+def test_channelizer_oracle_tone_and_call_pattern(rng):
+    N = 8
+    taps = orc.kaiser_lowpass(0.4 / N, 0.1 / N, 1e-3).astype(np.float32)
+    n = N * 600
+    for k in (0, 2, 5):
+        x = np.exp(2j * np.pi * (k / N) * np.arange(n)).astype(np.complex64)
+        y = orc.PfbChannelizer(N, taps, 1.0).run(x)
+        p = np.abs(y[:, -1])
+        assert y.shape == (N, n // N) and np.argmax(p) == k and p[k] > 0.9 and np.all(np.delete(p, k) < 1e-2)
+    # the call that completes the window fill consumes nothing (channelizer.rs:170-180)
+    ch = orc.PfbChannelizer(N, taps, 1.0)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    c, p, ca, _ = ch.work(x, 1 << 16)
+    assert (c, p, ca) == (0, 0, True)
+    c, p, ca, o = ch.work(x, 1 << 16)
+    assert (c, p) == (n, n // N) and o.shape == (N, n // N)
+    # oversampled by 2: decimation N/2, twice the output rate
+    y2 = orc.PfbChannelizer(N, taps, 2.0).run(x)
+    assert y2.shape == (N, n // (N // 2))
