@@ -75,6 +75,9 @@ SIGNATURES = {
     "b2s_chan_destroy": (None, [_vp]),
     "b2s_chan_decimation": (_sz, [_vp]),
     "b2s_chan_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _sz, _szp, _szp, _i32p]),
+    "b2s_synth_plan_c32": (_i32, [_vp, _sz, _f32p, _sz, _vpp]),
+    "b2s_synth_destroy": (None, [_vp]),
+    "b2s_synth_exec": (_i32, [_vp, _vp, _sz, _sz, _vp, _sz, _szp, _szp]),
     "b2s_mavg_create": (_i32, [_vp, _sz, _f32, _sz, _vpp]),
     "b2s_mavg_destroy": (None, [_vp]),
     "b2s_mavg_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp]),

@@ -369,6 +369,46 @@ class XlatingFir(Block):
             io.finished = True
 
 
+class PfbSynthesizer(Block):
+    """blocks::PfbSynthesizer (src/blocks/pfb/synthesizer.rs:32-144): N input streams (one channel-major
+    device buffer ``inputs`` [N, n] with per-call read position), one output stream."""
+
+    def __init__(self, num_channels: int, taps, ctx: Optional[Context] = None):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.ctx = ctx or default_context()
+        self.num_channels = int(num_channels)
+        self._h = C.c_void_p()
+        check(lib.b2s_synth_plan_c32(self.ctx.handle, self.num_channels, taps.ctypes.data_as(C.POINTER(C.c_float)),
+                                     taps.size, C.byref(self._h)), self.ctx.handle)
+        self.inputs = torch.zeros(self.num_channels, 0, dtype=torch.complex64, device="cuda")
+        self.in_pos = 0
+        self.inputs_finished = True
+        self.output = Writer(np.complex64)
+
+    def set_inputs(self, x):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.complex64))
+        self.inputs = t.to(device="cuda", dtype=torch.complex64).contiguous()
+        assert self.inputs.shape[0] == self.num_channels
+        self.in_pos = 0
+
+    def work(self, io: WorkIo):
+        n_in = self.inputs.shape[1] - self.in_pos
+        o = self.output.slice()
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        in_ptr = self.inputs.data_ptr() + 8 * self.in_pos
+        check(lib.b2s_synth_exec(self._h, C.c_void_p(in_ptr), self.inputs.shape[1], n_in, C.c_void_p(o.data_ptr()),
+                                 o.numel(), C.byref(c), C.byref(p)), self.ctx.handle)
+        self.in_pos += c.value
+        self.output.produce(p.value)
+        if n_in - c.value == 0 and self.inputs_finished:                          # :131-141
+            io.finished = True
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_synth_destroy(self._h)
+            self._h = None
+
+
 class MovingAvg(Block):
     """blocks::MovingAvg<WIDTH> (src/blocks/moving_avg.rs:24-116): exponential average per bin over
     consecutive WIDTH-item chunks, one output chunk every ``history_size`` input chunks."""

@@ -192,6 +192,15 @@ size_t  b2s_chan_decimation(const b2s_chan *c);
 int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, size_t out_stride, size_t n_out_cap,
                       size_t *consumed, size_t *produced_per_channel, int32_t *call_again);
 
+/* ---- PfbSynthesizer (≙ src/blocks/pfb/synthesizer.rs:52-144): N-point inverse FFT per
+ * input vector + polyphase FIR bank, N outputs per vector.  d_in is channel-major (stream w starts at
+ * d_in + w * in_stride items), n_in = the shortest input slice.  One exec == one Kernel::work call. */
+typedef struct b2s_synth b2s_synth;
+int32_t b2s_synth_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps, size_t ntaps, b2s_synth **out);
+void    b2s_synth_destroy(b2s_synth *s);
+int32_t b2s_synth_exec(b2s_synth *s, const void *d_in, size_t in_stride, size_t n_in, void *d_out, size_t n_out_cap,
+                       size_t *consumed_per_channel, size_t *produced);
+
 /* ---- MovingAvg<WIDTH> (≙ src/blocks/moving_avg.rs:24-116; SURVEY §8f-3, tail of the spectrum pipe
  * Fft(shift) -> |x|^2 -> MovingAvg).  f32 items; state (avg[WIDTH], chunk counter) kept on the device. */
 typedef struct b2s_mavg b2s_mavg;

@@ -370,6 +370,37 @@ class PfbChannelizer:
         return np.concatenate(outs, axis=1)
 
 
+class PfbSynthesizer:
+    """PfbSynthesizer state machine (src/blocks/pfb/synthesizer.rs:52-144)."""
+
+    def __init__(self, num_channels, taps):
+        taps = _as(taps, np.float32)
+        L = lib()
+        L.orc_synth_new.restype = C.c_void_p
+        L.orc_synth_new.argtypes = [C.c_size_t, _f32p, C.c_size_t]
+        L.orc_synth_free.restype = None
+        L.orc_synth_free.argtypes = [C.c_void_p]
+        L.orc_synth_work.restype = None
+        L.orc_synth_work.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, _szp, _szp]
+        self.N = num_channels
+        self._h = L.orc_synth_new(num_channels, _p32(taps), taps.size)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_synth_free(self._h)
+            self._h = None
+
+    def work(self, x, out_cap):
+        """x: [N, n] channel-major inputs. Returns (consumed_per_channel, produced, out)."""
+        xi = np.ascontiguousarray(x, dtype=np.complex64)
+        assert xi.shape[0] == self.N
+        out = np.zeros(max(out_cap, self.N) + self.N, np.complex64)
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        lib().orc_synth_work(self._h, _p32(xi.view(np.float32).reshape(-1)), xi.shape[1], xi.shape[1],
+                             _p32(out.view(np.float32)), out_cap, C.byref(c), C.byref(p))
+        return c.value, p.value, out[: p.value].copy()
+
+
 class MovingAvg:
     """MovingAvg<WIDTH> (src/blocks/moving_avg.rs:24-116)."""
 

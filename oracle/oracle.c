@@ -709,6 +709,61 @@ void orc_chan_work(orc_chan *s, const float *in, size_t n_in, float *out, size_t
 }
 
 /* ------------------------------------------------------------------------------------------
+ * PfbSynthesizer -- src/blocks/pfb/synthesizer.rs:52-144.  Inputs are channel-major:
+ * in[ch * in_stride + v]; n_in = the shortest input slice (:90).  "Parity unpinned".
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    size_t N, T;
+    float *arms;                 /* [N][T] utilities.rs order */
+    float *circ;                 /* [N][2T] complex */
+    size_t start_idx, missing;   /* all windows move in lockstep (one push each per vector) */
+    int all_filled;
+} orc_synth;
+
+orc_synth *orc_synth_new(size_t num_channels, const float *taps, size_t ntaps) {
+    orc_synth *s = (orc_synth *)calloc(1, sizeof(orc_synth));
+    size_t N = num_channels, T = (size_t)ceilf((float)ntaps / (float)N);
+    s->N = N; s->T = T;
+    s->arms = (float *)calloc(N * T, sizeof(float));
+    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) s->arms[i * T + j++] = taps[idx]; }
+    s->circ = (float *)calloc(N * 4 * T, sizeof(float));
+    s->start_idx = 0; s->missing = T; s->all_filled = 0;
+    return s;
+}
+void orc_synth_free(orc_synth *s) { if (s) { free(s->arms); free(s->circ); free(s); } }
+
+void orc_synth_work(orc_synth *s, const float *in, size_t in_stride, size_t n_in, float *out, size_t n_out_cap,
+                    size_t *consumed_per_channel, size_t *produced) {
+    size_t N = s->N, T = s->T, c = 0, p = 0;
+    double *br = (double *)malloc(4 * N * sizeof(double)), *bi = br + N, *yr = bi + N, *yi = yr + N;
+    while (n_in - c > 0 && (n_out_cap - p > N || !s->all_filled)) {                /* :95-97 */
+        for (size_t w = 0; w < N; w++) { br[w] = in[2 * (w * in_stride + c)]; bi[w] = in[2 * (w * in_stride + c) + 1]; }
+        c++;
+        dft_f64(br, bi, yr, yi, N, 1);                                             /* ifft.process (:104) */
+        long L = (long)T;
+        long idx = ((long)s->start_idx - (long)s->missing) % L; if (idx < 0) idx += L;
+        size_t missing_after = s->missing > 0 ? s->missing - 1 : 0;
+        size_t start_after = (s->start_idx + 1) % T;
+        for (size_t w = 0; w < N; w++) {
+            float *cw = s->circ + w * 4 * T;
+            float re = (float)yr[w], im = (float)yi[w];
+            cw[2 * idx] = re; cw[2 * idx + 1] = im; cw[2 * (idx + L)] = re; cw[2 * (idx + L) + 1] = im;   /* window.push */
+            if (missing_after == 0) {                                              /* window.filled() */
+                const float *win = cw + 2 * start_after;
+                const float *a = s->arms + w * T;
+                float ore = 0.0f, oim = 0.0f;
+                for (size_t t = 0; t < T; t++) { float tap = a[T - 1 - t]; ore = ore + win[2 * t] * tap; oim = oim + win[2 * t + 1] * tap; }
+                out[2 * p] = ore; out[2 * p + 1] = oim; p++;
+            }
+        }
+        s->missing = missing_after; s->start_idx = start_after;
+        if (!s->all_filled) s->all_filled = (s->missing == 0);
+    }
+    free(br);
+    *consumed_per_channel = c; *produced = p;
+}
+
+/* ------------------------------------------------------------------------------------------
  * MovingAvg<WIDTH> -- src/blocks/moving_avg.rs:72-115 (spectrum pipe tail).
  * state: avg[width] and the chunk counter *i (in/out).  Returns consumed/produced in items.
  * ---------------------------------------------------------------------------------------- */

@@ -120,6 +120,40 @@ def main():
         cap = n // 4 * L // M + L
         sec = timeit(lambda: r.filter.filter(x[: n // 4], y[:cap]), iters=5)
         report(f"resamp_{L}_{M}_c32", n // 4, 8 * (n // 4) + 8 * ((n // 4) * L // M), sec)
+    # XlatingFir, PfbChannelizer, spectrum pipe
+    xl = B.XlatingFir(4, 1000.0, 48000.0)
+    nx = n // 4
+
+    def run_xl():
+        c, p, st = xl.filter.filter(x[:nx], y[: nx // 4])
+        xl.rotator.rotate_inplace(y[:p])
+    sec = timeit(run_xl, iters=3, warm=1)
+    report("xlating_fir_d4_52taps", nx, 8 * nx + 8 * (nx // 4), sec, extra="includes the host replay of the rotator recurrence")
+    ctaps = (orc.kaiser_lowpass(0.4 / 64, 0.1 / 64, 1e-3)).astype(np.float32)[: 64 * 16]
+    ch = B.PfbChannelizer(64, ctaps, 1.0)
+    ch.reserve_outputs(n // 64 + 8)
+    ch.input.set(x[:n])
+    ch.work(B.WorkIo())                                   # window fill
+
+    def run_ch():
+        ch.input.pos, ch.produced = 0, 0
+        ch.work(B.WorkIo())
+    sec = timeit(run_ch, iters=5, warm=1)
+    report("pfb_channelizer_64ch_16taps", n, 16 * n, sec, extra="FIR bank + 64-pt IFFT + transpose (3 kernels)")
+    fft2 = B.Fft.with_options(2048, B.FftDirection.Forward, True, None)
+    mag = B.Apply(B.ApplyOp.NormSqr)
+    keep = B.MovingAvg(2048, 0.1, 3)
+    pw = torch.empty(n, dtype=torch.float32, device="cuda")
+    po = torch.empty(n // 3 + 4096, dtype=torch.float32, device="cuda")
+
+    def run_spec():
+        fft2.transform(x[:n], y[:n])
+        mag.apply(y[:n], pw)
+        keep.input.set(pw)
+        keep.output.data, keep.output.len = po, 0
+        keep.work(B.WorkIo())
+    sec = timeit(run_spec, iters=5, warm=1)
+    report("spectrum_pipe_fft2048_normsqr_mavg", n, 8 * n + 4 * (n // 3), sec, extra="unfused: 3 kernels, 32 B/sample of HBM traffic")
     # element-wise scale (the Vulkan/wgpu shader)
     sc = B.Apply(B.ApplyOp.ScaleF32, 12.0)
     sec = timeit(lambda: sc.apply(xr, yr))

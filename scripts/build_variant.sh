@@ -7,7 +7,7 @@ NAME=$1; EXTRA=$2
 mkdir -p ../variants build_$NAME
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ -I../../include -I. --expt-relaxed-constexpr $EXTRA"
 OBJS=""
-for f in abi fir_direct fir_tc fir_fft firdes fft apply resamp pfbarb rotator chan mavg ring; do
+for f in abi fir_direct fir_tc fir_fft firdes fft apply resamp pfbarb rotator chan synth mavg ring; do
   /usr/local/cuda/bin/nvcc $FLAGS -c $f.cu -o build_$NAME/$f.o &
   OBJS="$OBJS build_$NAME/$f.o"
 done
