@@ -4,11 +4,16 @@ is single-process, single-device).
 One process per GPU.  The stream is cut into contiguous time ranges: at step ``t`` rank ``r``
 of ``W`` owns samples ``[(t*W + r)*S, (t*W + r + 1)*S)``.  A FIR output needs the ``ntaps-1``
 inputs before it, so the only data-path exchange is the *overlap region*: every rank
-contributes the last ``ntaps-1`` samples of its chunk to one fixed-size NCCL all-gather
-(``(ntaps-1)*8`` bytes per rank, e.g. 2 KiB for 256 taps) and copies its left neighbour's
-tail into the halo slot in front of its own chunk (rank 0 takes rank ``W-1``'s tail of the
-previous step; at the very start of the stream there is no history, so the first chunk yields
-``S-(ntaps-1)`` outputs exactly like the reference, perf/fir/fir.rs:97).
+contributes the last ``H = ceil((ntaps-1)/D)*D`` samples of its chunk to one fixed-size NCCL
+all-gather (2 KiB per rank for 256 taps) and installs its left neighbour's tail as history in
+front of its own chunk (rank 0 takes rank ``W-1``'s tail of the previous step; at the very start
+of the stream there is no history, so the first chunk yields ``S-(ntaps-1)`` outputs exactly like
+the reference, perf/fir/fir.rs:97).
+
+The exchange is latency-bound (~tens of microseconds), so it is taken off the critical path: the
+all-gather is launched asynchronously, the outputs whose window lies entirely inside the rank's
+own chunk (all but the first ``H/D``) are computed meanwhile, and only a small second launch for
+the first ``H/D`` outputs waits for the neighbour's tail.
 
 The per-rank compute is the same C-ABI FIR plan as the single-GPU path; ``compute`` can be
 replaced (tests run this file's logic on CPU over gloo with the oracle as the kernel).
@@ -25,7 +30,7 @@ import torch.distributed as dist
 class ShardedFir:
     def __init__(self, taps, chunk_items: int, sample_dtype=np.complex64, decim: int = 1,
                  device: Optional[torch.device] = None, group=None,
-                 compute: Optional[Callable] = None, algo: int = 0):
+                 compute: Optional[Callable] = None, algo: int = 0, overlap: bool = True):
         self.taps = np.ascontiguousarray(taps)
         self.ntaps = int(self.taps.size)
         self.S = int(chunk_items)
@@ -37,7 +42,7 @@ class ShardedFir:
         self.halo = ((self.ntaps + self.decim - 2) // self.decim) * self.decim
         if self.S % self.decim:
             raise ValueError("chunk_items must be a multiple of decim so shard phases align")
-        if self.S < self.halo:
+        if self.S < self.halo + self.ntaps:
             raise ValueError("chunk shorter than the FIR history")
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -47,8 +52,11 @@ class ShardedFir:
         # [halo | chunk] contiguous so the kernel sees history + new samples as one slice
         self.xbuf = torch.zeros(self.halo + self.S, dtype=self.tdtype, device=self.device)
         self.tails = torch.zeros(self.world, max(self.halo, 1), dtype=self.tdtype, device=self.device)
+        self.my_tail = torch.zeros(max(self.halo, 1), dtype=self.tdtype, device=self.device)
+        self.prev_last_tail = torch.zeros(max(self.halo, 1), dtype=self.tdtype, device=self.device)
         self.have_history = False          # becomes True after the first step of the stream
         self.step_index = 0
+        self.overlap = bool(overlap)
         if compute is None:
             from .filters import DecimatingFirFilter
             self._filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, algo=algo)
@@ -60,37 +68,55 @@ class ShardedFir:
         """The rank's writable chunk (fill this with the step's samples)."""
         return self.xbuf[self.halo:]
 
-    def exchange_halo(self):
-        """All-gather of the overlap region; installs the left neighbour's tail as history."""
+    def _exchange(self, async_op: bool):
+        """All-gather of the overlap region (every rank's last H samples). Returns a work handle or None."""
         if self.halo == 0:
-            return
-        my_tail = self.xbuf[self.S:]                      # last `halo` samples of [halo|chunk]
-        if self.world > 1:
-            # complex tensors travel as their (re, im) float view
-            real = (lambda t: torch.view_as_real(t) if t.is_complex() else t)
-            dist.all_gather_into_tensor(real(self.tails).reshape(-1), real(my_tail.contiguous()).reshape(-1),
-                                        group=self.group)
-        else:
-            self.tails[0].copy_(my_tail)
+            return None
+        self.my_tail.copy_(self.xbuf[self.S:])           # last `halo` samples of [halo|chunk]
+        if self.world == 1:
+            self.tails[0].copy_(self.my_tail)
+            return None
+        # complex tensors travel as their (re, im) float view
+        real = (lambda t: torch.view_as_real(t) if t.is_complex() else t)
+        return dist.all_gather_into_tensor(real(self.tails).reshape(-1), real(self.my_tail).reshape(-1),
+                                           group=self.group, async_op=async_op)
 
     def step(self, out: torch.Tensor):
         """Filter this step's chunk (already written into ``self.chunk``).
 
         Returns (consumed, produced, status).  ``out`` must hold ``S // decim`` items.
         """
-        # history for this chunk: left neighbour's tail of THIS step (r > 0), or rank W-1's
-        # tail of the PREVIOUS step (r == 0), which `tails` still holds from the last exchange.
-        if self.rank == 0:
-            if self.have_history and self.halo:
-                self.xbuf[:self.halo].copy_(self.tails[self.world - 1][:self.halo])
-            self.exchange_halo()
-        else:
-            self.exchange_halo()
-            if self.halo:
-                self.xbuf[:self.halo].copy_(self.tails[self.rank - 1][:self.halo])
+        H, D, N = self.halo, self.decim, self.ntaps
         first_of_stream = self.rank == 0 and not self.have_history
-        src = self.xbuf[self.halo:] if first_of_stream else self.xbuf
-        res = self.compute(src, out)
+        work = self._exchange(async_op=self.overlap)
+        if first_of_stream:
+            res = self.compute(self.xbuf[H:], out)                       # no history: S-(ntaps-1) outputs
+        elif self.rank == 0:
+            # history = rank W-1's tail of the PREVIOUS step (saved before this step's gather started)
+            if H:
+                self.xbuf[:H].copy_(self.prev_last_tail[:H])
+            res = self.compute(self.xbuf, out)
+        elif H == 0:
+            res = self.compute(self.xbuf, out)
+        elif self.overlap:
+            nh = H // D                                                  # outputs that need the neighbour's tail
+            c1, p1, st = self.compute(self.xbuf[H:], out[nh:])           # windows fully inside the own chunk
+            if work is not None:
+                work.wait()
+                work = None
+            self.xbuf[:H].copy_(self.tails[self.rank - 1][:H])
+            c0, p0, _ = self.compute(self.xbuf[:H + N - 1], out[:nh])    # the first H/D outputs
+            res = (c0 + c1, p0 + p1, st)
+        else:
+            if work is not None:
+                work.wait()
+                work = None
+            self.xbuf[:H].copy_(self.tails[self.rank - 1][:H])
+            res = self.compute(self.xbuf, out)
+        if work is not None:
+            work.wait()
+        if self.rank == 0 and H:
+            self.prev_last_tail.copy_(self.tails[self.world - 1])        # history for the next step
         self.have_history = True
         self.step_index += 1
         return res
