@@ -35,7 +35,10 @@
 namespace {
 
 constexpr int kStages = 2;                  // bf16 operand stages (72 KiB each)
-constexpr int kRawSlots = 8;                // raw f32 staging ring, 8 KiB per slot (TMA bulk copies)
+#ifndef B2S_RAW_SLOTS
+#define B2S_RAW_SLOTS 8
+#endif
+constexpr int kRawSlots = B2S_RAW_SLOTS;    // raw f32 staging ring, 8 KiB per slot (TMA bulk copies)
 constexpr int kRawSlotBytes = 8192;
 constexpr int kNumProducerThreads = 256;    // 8 converter warps
 constexpr int kNumEpilogueThreads = 256;    // 8 warps: two per TMEM lane quarter, 64 columns each
