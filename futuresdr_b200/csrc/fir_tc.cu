@@ -324,22 +324,30 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         __syncwarp();
     } else if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ================================ CONVERTERS ===========================================
-        // 256 threads; thread t owns float4 #t and #(t+256) of every raw slot: its position inside a
-        // 128-item block is fixed, so the 128B-swizzle arithmetic is per-thread constant.  Per float4:
-        // one LDS.128, the bf16 hi/lo split, and 4 (8 for aliased rows) 32-bit swizzled stores.
+        // 256 threads; thread t owns float4 #t and #(t+256) of every raw slot.  Its position inside a
+        // 128-item block (fo) and its row inside a slot (rowsel) never change, and the slot / float4
+        // loops are fully unrolled, so every shared-memory address is
+        //     stage base + per-thread constant + compile-time constant + one of 8 precomputed swizzle offsets.
+        // Per float4: one LDS.128, two XU conversions per value pair, 4 (8 for aliased rows) 32-bit stores.
+        // (The first version of this loop spent ~120 instructions per float4 on address arithmetic and
+        // bounds predicates and was the busiest part of the SM; interior tiles now take a check-free path.)
         const int tid = threadIdx.x - 32 * kProdWarp0;                   // 0..255
         const int fo = tid % F4_PER_BLOCK, rowsel = tid / F4_PER_BLOCK;  // rowsel 0..3 (complex) / 0..7 (real)
-        constexpr int ROWS_PER_PASS = kNumProducerThreads / F4_PER_BLOCK; // blocks covered by 256 threads: 4 / 8
         const int kc = COMPLEX ? (fo >> 5) : (fo >> 4);
         const int c16 = COMPLEX ? ((fo & 31) >> 2) : ((fo & 15) >> 1);
         const int wofs = COMPLEX ? (fo & 3) * 4 : (fo & 1) * 8;
-        int stage = 0, rs = 0;
-        uint32_t phase = 0, rphase = 0;
-        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
-            const long long item0 = (long long)tile * TILE_ITEMS;
-            const bool interior = item0 + (long long)in_blocks * 128 <= prm.n_in;
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            unsigned char *colp = gen_base + stage * kStageBytes + kc * chunk_bytes + wofs;
+        const uint32_t t_off = (uint32_t)(kc * chunk_bytes + wofs + rowsel * 1024);
+        uint32_t xj[8];                                                   // row j: j*128 + ((c16 ^ j) << 4)
+#pragma unroll
+        for (int j = 0; j < 8; j++) xj[j] = (uint32_t)(j * 128 + ((c16 ^ j) << 4));
+        const bool alias_thread = rowsel < DK - 1;                        // this thread's rows alias into atoms 16, 17
+        const uint32_t sb = (uint32_t)split_bytes;
+
+        // compile-time geometry of (slot s, float4 i): block bl = BLOCKS_PER_SLOT*s + rowsel + ROWS*i = gamma + 16*seq
+        //   complex: gamma = 8*(s&1) + 4*i + rowsel, seq = s>>1 ;  real: gamma = 8*i + rowsel, seq = s
+        auto convert_tile = [&](auto interior_c, unsigned char *stage_ptr, long long item0, int &rs, uint32_t &rphase) {
+            constexpr bool INTERIOR = decltype(interior_c)::value;
+            unsigned char *tp = stage_ptr + t_off;
 #pragma unroll
             for (int s = 0; s < SLOTS_PER_TILE; s++) {
                 if (s * BLOCKS_PER_SLOT >= in_blocks) break;
@@ -352,13 +360,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                 if (++rs == kRawSlots) { rs = 0; rphase ^= 1; }
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const int bl = s * BLOCKS_PER_SLOT + rowsel + ROWS_PER_PASS * i;   // block row inside the tile
-                    if (bl >= in_blocks || (prm.flags & 8)) continue;   // flags bit3: tuning switch, skip conversion
-                    if (!interior) {
-                        // last tile: the bulk copy moved whole 16-byte units only; the <= 3 trailing floats
-                        // are fetched directly, everything beyond the input is zero
+                    constexpr int ROWS = COMPLEX ? 4 : 8;
+                    const int g_ct = COMPLEX ? (8 * (s & 1) + 4 * i) : (8 * i);          // compile-time after unrolling
+                    const int seq = COMPLEX ? (s >> 1) : s;
+                    const bool alias_ct = COMPLEX ? ((s & 1) == 0 && i == 0 && s >= 2) : (i == 0 && s >= 1);
+                    if (s == SLOTS_PER_TILE - 1) {                       // only the last slot can run past the tile's input
+                        if (s * BLOCKS_PER_SLOT + rowsel + ROWS * i >= in_blocks) continue;
+                    }
+                    if (prm.flags & 8) continue;                         // tuning switch: skip conversion
+                    if constexpr (!INTERIOR) {
+                        // last tile: the bulk copy moved whole 16-byte units only; the <= 3 trailing floats are
+                        // fetched directly, everything beyond the input is zero
+                        const int bl = s * BLOCKS_PER_SLOT + rowsel + ROWS * i;
                         const long long it = item0 + (long long)bl * 128 + (long long)fo * (COMPLEX ? 2 : 4);
-                        const long long gf = it * (COMPLEX ? 2 : 1);                       // global float index of e[0]
+                        const long long gf = it * (COMPLEX ? 2 : 1);
                         const long long total_f = prm.n_in * (COMPLEX ? 2 : 1), copied_f = total_f & ~3ll;
                         float *e = reinterpret_cast<float *>(&v[i]);
 #pragma unroll
@@ -367,50 +382,54 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                             else if (gf + c >= copied_f) e[c] = prm.in[gf + c];
                         }
                     }
-                    // bl = gamma + 16*seq.  complex: gamma = 8*(s&1) + rowsel + 4*i, seq = s>>1 ; real: gamma = rowsel + 8*i, seq = s
-                    const int g0 = bl & (kAtomsOut - 1), s0 = bl >> 4;
                     if constexpr (COMPLEX) {
-                        uint32_t rh, rl, ih, il;
+                        uint32_t rh, rl, ih, il;                          // float4 = (re0, im0, re1, im1)
                         split2(v[i].x, v[i].z, rh, rl);
                         split2(v[i].y, v[i].w, ih, il);
-                        if (s0 < NSEQ) {
-                            const int jre = 2 * s0, jim = jre + 1;
-                            unsigned char *pre = colp + g0 * 1024 + jre * 128 + ((c16 ^ jre) << 4);
-                            unsigned char *pim = colp + g0 * 1024 + jim * 128 + ((c16 ^ jim) << 4);
-                            *reinterpret_cast<uint32_t *>(pre) = rh;
-                            *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
-                            *reinterpret_cast<uint32_t *>(pim) = ih;
-                            *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
+                        if (seq < NSEQ) {
+                            unsigned char *q = tp + g_ct * 1024;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * (seq & 3)]) = rh;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * (seq & 3)] + sb) = rl;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * (seq & 3) + 1]) = ih;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * (seq & 3) + 1] + sb) = il;
                         }
-                        if (s0 >= 1 && g0 + kAtomsOut < atoms) {         // alias row (gamma+16, jb-1)
-                            const int jre = 2 * (s0 - 1), jim = jre + 1;
-                            unsigned char *pre = colp + (g0 + kAtomsOut) * 1024 + jre * 128 + ((c16 ^ jre) << 4);
-                            unsigned char *pim = colp + (g0 + kAtomsOut) * 1024 + jim * 128 + ((c16 ^ jim) << 4);
-                            *reinterpret_cast<uint32_t *>(pre) = rh;
-                            *reinterpret_cast<uint32_t *>(pre + split_bytes) = rl;
-                            *reinterpret_cast<uint32_t *>(pim) = ih;
-                            *reinterpret_cast<uint32_t *>(pim + split_bytes) = il;
+                        if (alias_ct && alias_thread) {                   // alias row (gamma+16, seq-1)
+                            unsigned char *q = tp + (g_ct + kAtomsOut) * 1024;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * ((seq - 1) & 3)]) = rh;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * ((seq - 1) & 3)] + sb) = rl;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * ((seq - 1) & 3) + 1]) = ih;
+                            *reinterpret_cast<uint32_t *>(q + xj[2 * ((seq - 1) & 3) + 1] + sb) = il;
                         }
                     } else {
-                        uint32_t h0, l0, h1, l1;
+                        uint32_t h0, l0, h1, l1;                          // float4 = 4 consecutive samples
                         split2(v[i].x, v[i].y, h0, l0);
                         split2(v[i].z, v[i].w, h1, l1);
-                        if (s0 < NSEQ) {
-                            unsigned char *pp = colp + g0 * 1024 + s0 * 128 + ((c16 ^ s0) << 4);
-                            *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
-                            *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
+                        if (seq < NSEQ) {
+                            unsigned char *q = tp + g_ct * 1024 + xj[seq & 7];
+                            *reinterpret_cast<uint2 *>(q) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2 *>(q + sb) = make_uint2(l0, l1);
                         }
-                        if (s0 >= 1 && g0 + kAtomsOut < atoms) {
-                            const int j = s0 - 1;
-                            unsigned char *pp = colp + (g0 + kAtomsOut) * 1024 + j * 128 + ((c16 ^ j) << 4);
-                            *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
-                            *reinterpret_cast<uint2 *>(pp + split_bytes) = make_uint2(l0, l1);
+                        if (alias_ct && alias_thread) {
+                            unsigned char *q = tp + (g_ct + kAtomsOut) * 1024 + xj[(seq - 1) & 7];
+                            *reinterpret_cast<uint2 *>(q) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2 *>(q + sb) = make_uint2(l0, l1);
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(rempty_bar(rs_cur));          // values consumed: slot may be refilled
             }
+        };
+
+        int stage = 0, rs = 0;
+        uint32_t phase = 0, rphase = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+            const long long item0 = (long long)tile * TILE_ITEMS;
+            const bool interior = item0 + (long long)in_blocks * 128 <= prm.n_in;
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            unsigned char *stage_ptr = gen_base + stage * kStageBytes;
+            if (interior) convert_tile(std::true_type{}, stage_ptr, item0, rs, rphase);
+            else convert_tile(std::false_type{}, stage_ptr, item0, rs, rphase);
             fence_proxy_async();                     // generic-proxy stores -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
