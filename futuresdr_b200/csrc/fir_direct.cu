@@ -100,6 +100,48 @@ fir_direct_kernel(const S *__restrict__ in, S *__restrict__ out, const T *__rest
             }
             *reinterpret_cast<float4 *>(xs + swz(c) * 16) = v;
         }
+    } else if (vec_ok) {
+        // Decimator: 16-byte loads, four in flight per thread (the scalar loop below kept too few bytes
+        // in flight to cover HBM latency: 43 % of the roofline for D = 4), then scatter the EPC items of
+        // each chunk into their phase rows.  (q, m) of a thread's chunks advance by a fixed step, so
+        // there is one integer division per thread, not per item.  s0 * sizeof(S) is a multiple of 16.
+        const int total = D * W;
+        const int nchunks = (total + EPC - 1) / EPC;
+        constexpr int UNR = 4;
+        int q = (tid * EPC) % D, m = (tid * EPC) / D;
+        const int dq = (THREADS * EPC) % D, dm = (THREADS * EPC) / D;
+        for (int c0 = tid; c0 < nchunks; c0 += THREADS * UNR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int c = c0 + u * THREADS;
+                const long long s = s0 + (long long)c * EPC;
+                if (c < nchunks && s + EPC <= n_in) {
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(in + s));
+                } else {
+                    S tmp[EPC];
+#pragma unroll
+                    for (int e = 0; e < EPC; e++) tmp[e] = (c < nchunks && s + e < n_in) ? in[s + e] : zero_of<S>();
+                    v[u] = *reinterpret_cast<float4 *>(tmp);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int c = c0 + u * THREADS;
+                const S *items = reinterpret_cast<const S *>(&v[u]);
+                int qe = q, me = m;
+#pragma unroll
+                for (int e = 0; e < EPC; e++) {
+                    if (c < nchunks && c * EPC + e < total) {
+                        const int chunk = me / EPC, el = me % EPC;
+                        *reinterpret_cast<S *>(xs + ((size_t)qe * pitch + (swz(chunk) ^ (qe & 7)) * EPC + el) * sizeof(S)) = items[e];
+                    }
+                    if (++qe == D) { qe = 0; me++; }
+                }
+                q += dq; m += dm;
+                if (q >= D) { q -= D; m += 1; }
+            }
+        }
     } else {
         // item j of the tile -> phase q = j % D, row index m = j / D (s0 is a multiple of D)
         const int total = D * W;

@@ -1,9 +1,9 @@
-// fir_tc.cu -- tcgen05 (5th-gen tensor core) FIR for long real-tap filters on sm_100a.
+// fir_tc.cu -- tcgen05 (5th-gen tensor core) FIR for 16..257 real taps on sm_100a.
 //
 // Computes the same  o[k] = sum_t i[k+t] * taps[N-1-t]  as crates/futuredsp/src/fir.rs:77-88
 // (Complex<f32> or f32 samples, f32 taps, no decimation) as a block-Toeplitz GEMM:
 //
-//      D[p][c] = sum_kappa A[p][kappa] * B[c][kappa]            (M=128, N=64, K=128*DK)
+//      D[p][c] = sum_kappa A[p][kappa] * B[c][kappa]            (M = 128, N = 128, K = 128*DK <= 384)
 //      A[p][kappa] = g[kappa - p]   (g[t] = taps[N-1-t], zero outside [0,N))   -- "taps, Toeplitz"
 //      B[c][kappa] = w_c[kappa]     (column c = one 128-sample block of the re- or im-stream,
 //                                    extended by the following blocks)         -- "samples"
@@ -17,13 +17,18 @@
 //    TMEM.  Dropped terms are O(2^-17) relative per product (DESIGN.md "tensor FIR numerics").
 //  * B rows are K-major, 128-byte swizzled.  K-block d of row (stream, block b) is row
 //    (stream, block b+d): a shifted view of the same tile.  Rows are stored so that the shift
-//    is a whole 8-row swizzle atom: physical atom gamma holds blocks {gamma + 8*jb}; the view
-//    for shift d starts at atom d (descriptor base + 1024*d bytes).  Atoms 8,9 duplicate the
-//    rows they alias (25 % extra conversion work, no extra HBM traffic).
-//  * warp roles: warps 0-3 producers (coalesced LDG.128 -> split to bf16 hi/lo -> swizzled
-//    st.shared), warps 4-7 epilogue (tcgen05.ld -> coalesced float2 stores; lane p of TMEM is
-//    output phase p, adjacent columns are re/im of the same block), warp 8 issues the MMAs.
-//    smem stages and the two TMEM accumulators are handed over with mbarriers.
+//    is a whole 8-row swizzle atom: physical atom gamma holds blocks {gamma + 16*jb}; the view
+//    for shift d starts at atom d (descriptor base + 1024*d bytes).  Atoms 16, 17 duplicate the
+//    rows they alias (12 % extra conversion work, no extra HBM traffic).
+//  * 18 warps, one persistent CTA per SM, everything handed over with mbarriers:
+//      warp 17    TMA loader : cp.async.bulk (UBLKCP) of the raw f32 samples into a 6 x 8 KiB ring
+//      warps 8-15 converters : LDS.128 -> bf16 hi/lo split (cvt.rn.bf16x2) -> swizzled st.shared
+//                              into one of two 72 KiB operand stages
+//      warp 16    MMA issuer : 72 tcgen05.mma per tile (DK x 8 K-steps x 3 products), one elected thread
+//      warps 0-7  epilogue   : tcgen05.ld -> 16 KiB staging -> cp.async.bulk shared->global stores
+//  * What bounds it (profiles/README.md): with 256 taps the tensor pipe is busy 86 %
+//    of the time and the SM clock sits at ~1.4 GHz under the board power cap (3 products x K = 384 is
+//    0.31 TFLOP per 64 Mi-sample chunk); below ~130 taps the HBM stream is the bound.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -36,7 +41,7 @@ namespace {
 
 constexpr int kStages = 2;                  // bf16 operand stages (72 KiB each)
 #ifndef B2S_RAW_SLOTS
-#define B2S_RAW_SLOTS 8
+#define B2S_RAW_SLOTS 6
 #endif
 constexpr int kRawSlots = B2S_RAW_SLOTS;    // raw f32 staging ring, 8 KiB per slot (TMA bulk copies)
 constexpr int kRawSlotBytes = 8192;
@@ -54,10 +59,38 @@ constexpr int kNTile = 8 * kAtomsOut;
 constexpr int kMaxDK = 3;                    // K <= 384  (TMEM: K columns of taps + 128 of accumulators)
 constexpr int kSplitBytesMax = (kAtomsOut + kMaxDK - 1) * 1024 * 2;   // per split: 2 K-chunks x 18 atoms
 constexpr int kStageBytes = 2 * kSplitBytesMax;                       // hi + lo = 72 KiB
-constexpr int kSmemTC = kStages * kStageBytes + kRawSlots * kRawSlotBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kOutStageBytes = 16384;        // output staging: 16 blocks of 128 complex items (one bulk store), double-buffered
+constexpr int kOutStages = 2;
+constexpr int kTapsSmemBytes = 1040;         // <= 257 reversed taps staged once for the Toeplitz fill
+constexpr int kSmemTC = kStages * kStageBytes + kRawSlots * kRawSlotBytes + kOutStages * kOutStageBytes + 1024 /*align*/ +
+                        256 /*barriers*/ + kTapsSmemBytes;
+static_assert(kSmemTC <= 227 * 1024, "tensor FIR shared memory exceeds the 227 KiB per-CTA limit");
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Optional per-role cycle accounting (build with -DB2S_TC_TIMING, run with B2S_TC_TIMING_DUMP=1): every role's
+// lane 0 accumulates clock64() laps into 16 counters per CTA; scripts/build_variant.sh builds the variant.
+// epilogue store flavour: plain (default) or streaming (st.global.cs, -DB2S_TC_ST_CS) -- A/B switch
+#ifdef B2S_TC_ST_CS
+#define B2S_TC_STORE(ptr, val) __stcs((ptr), (val))
+#else
+#define B2S_TC_STORE(ptr, val) (*(ptr) = (val))
+#endif
+#ifdef B2S_TC_TIMING
+__device__ long long g_tc_timing[256 * 16];
+#define TCT_DECL(n) long long tct_[n] = {}; long long tct_t0_ = clock64();
+#define TCT_LAP(i) { const long long t_ = clock64(); tct_[i] += t_ - tct_t0_; tct_t0_ = t_; }
+#define TCT_DUMP(base, n) { for (int i_ = 0; i_ < (n); i_++) g_tc_timing[blockIdx.x * 16 + (base) + i_] = tct_[i_]; }
+#define TCT_START const long long tct_k0_ = clock64();
+#define TCT_MARK(i) { g_tc_timing[blockIdx.x * 16 + (i)] = clock64() - tct_k0_; }
+#else
+#define TCT_START
+#define TCT_MARK(i) {}
+#define TCT_DECL(n)
+#define TCT_LAP(i) {}
+#define TCT_DUMP(base, n) {}
+#endif
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -77,6 +110,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// one thread of a converged warp; unlike `lane == 0` the compiler knows exactly one thread is active, so
+// uniform-datapath instructions (UTCHMMA, UBLKCP) are emitted bare instead of inside an ELECT retry loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+#ifdef B2S_TC_NO_ELECT
+    pred = (threadIdx.x & 31) == 0;             // A/B switch: the plain lane-0 guard
+#else
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+#endif
+    return pred != 0;
+}
+// shared -> global bulk copy (TMA store, SASS UBLKCP.G.S) in the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kNumEpilogueThreads) : "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -186,6 +238,7 @@ struct TcParams {
     int DK;               // K blocks of 128
     int num_tiles;
     int flags;            // bit0: swap bf16 halves of the TMEM A words (bring-up switch)
+    int out_bulk;         // out is 16-byte aligned: interior tiles leave through bulk (TMA) stores
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -201,13 +254,16 @@ struct TcParams {
 template <bool COMPLEX>
 __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams prm) {
     extern __shared__ unsigned char smem_raw[];
+    TCT_START
     // 1024-byte alignment for the 128B-swizzle atoms
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char *gen_base = smem_raw + (base - raw);
     const uint32_t raw_base = base + kStages * kStageBytes;           // raw f32 ring
     unsigned char *raw_gen = gen_base + kStages * kStageBytes;
-    const uint32_t bar_base = raw_base + kRawSlots * kRawSlotBytes;
+    const uint32_t ost_base = raw_base + kRawSlots * kRawSlotBytes;   // output staging (epilogue -> bulk stores)
+    unsigned char *ost_gen = raw_gen + kRawSlots * kRawSlotBytes;
+    const uint32_t bar_base = ost_base + kOutStages * kOutStageBytes;
     // barriers: full[kStages], empty[kStages], tfull[2], tempty[2], rfull[kRawSlots], rempty[kRawSlots], tmem slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -218,7 +274,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
     constexpr int kNumBars = 2 * kStages + 4 + 2 * kRawSlots;
     const uint32_t tmem_slot = bar_base + 8u * kNumBars;
     volatile uint32_t *tmem_slot_gen = reinterpret_cast<volatile uint32_t *>(
-        gen_base + kStages * kStageBytes + kRawSlots * kRawSlotBytes + 8 * kNumBars);
+        gen_base + kStages * kStageBytes + kRawSlots * kRawSlotBytes + kOutStages * kOutStageBytes + 8 * kNumBars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int DK = prm.DK, K = 128 * DK;
@@ -240,13 +296,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         __syncwarp();
         tmem_alloc(tmem_slot, 512);
     }
+    // reversed taps -> shared memory (one coalesced pass; the Toeplitz fill below reads them 48 times per lane)
+    float *gs = reinterpret_cast<float *>(gen_base + kStages * kStageBytes + kRawSlots * kRawSlotBytes +
+                                          kOutStages * kOutStageBytes + 256);
+    for (int i = threadIdx.x; i < prm.ntaps; i += kThreadsTC) gs[i] = __ldg(prm.g + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
     const uint32_t tmem_acc = tmem + (uint32_t)K;    // columns [K, 512): accumulators
 
-    // ---- one-time: Toeplitz taps into TMEM (epilogue warps own lanes 32*(warp%4)...)
+    // ---- one-time: Toeplitz taps into TMEM (epilogue warps 0..3 own lanes 32*warp..).  Only the MMA warp
+    // depends on it, so it alone waits (named barrier 2: 4 filler warps + the MMA warp); the TMA loader and
+    // the converters start streaming the first tiles while the table is being written.
     if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
         const int q = warp - kEpiWarp0, p = 32 * q + lane;   // TMEM lane = output phase p
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
@@ -255,8 +317,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int k0 = 2 * (c0 + i) - p, k1 = k0 + 1;
-                const float g0 = (k0 >= 0 && k0 < prm.ntaps) ? __ldg(prm.g + k0) : 0.0f;
-                const float g1 = (k1 >= 0 && k1 < prm.ntaps) ? __ldg(prm.g + k1) : 0.0f;
+                const float g0 = (k0 >= 0 && k0 < prm.ntaps) ? gs[k0] : 0.0f;
+                const float g1 = (k1 >= 0 && k1 < prm.ntaps) ? gs[k1] : 0.0f;
                 if (prm.flags & 1) split2(g1, g0, hi[i], lo[i]);
                 else split2(g0, g1, hi[i], lo[i]);
             }
@@ -264,10 +326,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             tmem_st8(lane_addr + (uint32_t)(K / 2 + c0), lo);
         }
         tmem_wait_st();
+        tc_fence_before();
+        asm volatile("bar.sync 2, 160;" ::: "memory");
+    } else if (warp == kMmaWarp) {
+        asm volatile("bar.sync 2, 160;" ::: "memory");
+        tc_fence_after();
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
 
     // A tile's contiguous input span (TILE_BLOCKS + DK - 1 blocks of 128 items) travels through the raw
     // ring in slots of 8 KiB = 512 float4 (8 complex blocks / 16 real blocks); 9 slots per tile.
@@ -282,23 +346,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         // One thread streams the input with bulk async copies (cp.async.bulk, UBLKCP): the copies
         // complete on the slot's mbarrier (complete_tx), so HBM latency is absorbed by the 64 KiB
         // ring and never by a converter warp's registers.
-        if (lane == 0) {
+        if (elect_one()) {
             int rs = 0;
             uint32_t rphase = 0;
-            const long long tile_in_items = (long long)in_blocks * 128;
-            auto prefetch_tile = [&](int tile) {     // whole-tile L2 prefetch, two tiles ahead of the ring
-                if (tile >= prm.num_tiles) return;
-                const long long i0 = (long long)tile * TILE_ITEMS;
-                long long items = prm.n_in - i0;
-                if (items > tile_in_items) items = tile_in_items;
-                const uint32_t bytes = (uint32_t)((items * ITEM_BYTES) & ~15ll);
-                if (bytes == 0) return;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(prm.in + (COMPLEX ? 2 : 1) * i0), "r"(bytes) : "memory");
-            };
-            prefetch_tile(blockIdx.x + gridDim.x);
+            TCT_DECL(2)
+            // (A whole-tile cp.async.bulk.prefetch.L2 two tiles ahead was tried: 63 % L2 read hit rate, but
+            // 1.3 % SLOWER -- the ring already covers HBM latency and the kernel runs power-capped, so the
+            // extra L2 traffic only costs clock.)
             for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
                 const long long item0 = (long long)tile * TILE_ITEMS;
-                prefetch_tile(tile + 2 * gridDim.x);
 #pragma unroll 1
                 for (int s = 0; s < SLOTS_PER_TILE; s++) {
                     const int blk_first = s * BLOCKS_PER_SLOT;
@@ -308,7 +364,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                     long long items = (long long)nblk * 128;
                     if (it0 + items > prm.n_in) items = prm.n_in - it0;
                     long long bytes = items > 0 ? ((items * ITEM_BYTES) & ~15ll) : 0;    // whole 16-byte units
+                    TCT_LAP(1)
                     mbar_wait(rempty_bar(rs), rphase ^ 1);
+                    TCT_LAP(0)
                     if (bytes > 0) {
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rfull_bar(rs)), "r"((uint32_t)bytes) : "memory");
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -320,6 +378,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                     if (++rs == kRawSlots) { rs = 0; rphase ^= 1; }
                 }
             }
+            TCT_DUMP(9, 2)
         }
         __syncwarp();
     } else if (warp >= kProdWarp0 && warp < kMmaWarp) {
@@ -342,6 +401,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         for (int j = 0; j < 8; j++) xj[j] = (uint32_t)(j * 128 + ((c16 ^ j) << 4));
         const bool alias_thread = rowsel < DK - 1;                        // this thread's rows alias into atoms 16, 17
         const uint32_t sb = (uint32_t)split_bytes;
+        TCT_DECL(3)
 
         // compile-time geometry of (slot s, float4 i): block bl = BLOCKS_PER_SLOT*s + rowsel + ROWS*i = gamma + 16*seq
         //   complex: gamma = 8*(s&1) + 4*i + rowsel, seq = s>>1 ;  real: gamma = 8*i + rowsel, seq = s
@@ -351,7 +411,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 #pragma unroll
             for (int s = 0; s < SLOTS_PER_TILE; s++) {
                 if (s * BLOCKS_PER_SLOT >= in_blocks) break;
+                TCT_LAP(1)
                 mbar_wait(rfull_bar(rs), rphase);
+                TCT_LAP(2)
                 const float4 *raw = reinterpret_cast<const float4 *>(raw_gen + rs * kRawSlotBytes);
                 float4 v[2];
                 v[0] = raw[tid];
@@ -426,7 +488,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             const long long item0 = (long long)tile * TILE_ITEMS;
             const bool interior = item0 + (long long)in_blocks * 128 <= prm.n_in;
+            TCT_LAP(1)
             mbar_wait(empty_bar(stage), phase ^ 1);
+            TCT_LAP(0)
             unsigned char *stage_ptr = gen_base + stage * kStageBytes;
             if (interior) convert_tile(std::true_type{}, stage_ptr, item0, rs, rphase);
             else convert_tile(std::false_type{}, stage_ptr, item0, rs, rphase);
@@ -435,15 +499,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if (tid == 0) TCT_DUMP(6, 3)
     } else if (warp == kMmaWarp) {
         // ================================ MMA ISSUER ===========================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc(128, kNTile);
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
+            TCT_DECL(3)
+            TCT_MARK(11)
             for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+                TCT_LAP(2)
                 mbar_wait(full_bar(stage), phase);
+                TCT_LAP(0)
                 mbar_wait(tempty_bar(acc), accphase ^ 1);
+                TCT_LAP(1)
                 tc_fence_after();
                 const uint32_t sbase = base + stage * kStageBytes;
                 const uint32_t d_tmem = tmem_acc + (uint32_t)(kNTile * acc);
@@ -453,6 +523,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                     for (int kc = 0; kc < 2; kc++) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
+                            // Toeplitz columns kappa >= ntaps + 127 hold no tap: skip those K-steps
+                            if (d * 128 + kc * 64 + ks * 16 >= prm.ntaps + 127) continue;
                             const uint32_t kcol = (uint32_t)(d * 64 + kc * 32 + ks * 8);       // A column (2 bf16 / column)
                             const uint32_t boff = (uint32_t)(kc * chunk_bytes + d * 1024 + ks * 32);
                             const uint64_t bh = make_b_desc(sbase + boff);
@@ -469,20 +541,32 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                 if (++acc == nacc) { acc = 0; accphase ^= 1; }
             }
+            TCT_DUMP(0, 3)
+            TCT_MARK(12)
         }
         __syncwarp();
     } else {
         // ================================ EPILOGUE =============================================
         // 8 warps: warp w serves TMEM lanes 32*(w%4).. and column half (w-8)/4.  Each warp pulls its
-        // 64 columns with two back-to-back tcgen05.ld, releases the accumulator as soon as they
-        // have landed (the single-accumulator K=384 case stalls the MMA warp until then), and only
-        // then streams the results out: lane p holds y[128*b + p], adjacent columns are (re, im)
-        // of the same block, so every store instruction writes 256 contiguous bytes.
+        // 64 columns with two back-to-back tcgen05.ld and releases the accumulator as soon as they
+        // have landed (the single-accumulator K=384 case stalls the MMA warp until then).
+        // Lane p holds y[128*b + p]; columns sharing jb (the sub-sequence index) belong to 16 consecutive
+        // blocks, i.e. ONE contiguous 16 KiB (complex) / 8 KiB (real) span of the output.  Interior tiles
+        // therefore leave in NSEQ rounds: the 8 warps lay the span out in a staging buffer (every store
+        // instruction writes a contiguous row segment, conflict-free), one thread hands it to the
+        // TMA as a single bulk store, and the next round fills the other buffer meanwhile.  Per-lane
+        // 8-byte global stores (the previous epilogue, still used for the ragged last tile and for
+        // unaligned outputs) kept the warps stalled on the LSU for ~40 % of a tile period.
         const int ew = warp - kEpiWarp0, q = ew & 3, half = ew >> 2, p = 32 * q + lane;
-        int acc = 0;
+        const bool store_thread = threadIdx.x == 32 * kEpiWarp0;
+        constexpr uint32_t ROUND_BYTES = kAtomsOut * 128 * ITEM_BYTES;          // 16 blocks
+        int acc = 0, obuf = 0;
         uint32_t accphase = 0;
+        TCT_DECL(3)
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+            TCT_LAP(2)
             mbar_wait(tfull_bar(acc), accphase);
+            TCT_LAP(0)
             tc_fence_after();
             const uint32_t taddr = tmem_acc + (uint32_t)(kNTile * acc + 64 * half) + ((uint32_t)(32 * q) << 16);
             uint32_t v[2][32];
@@ -492,9 +576,38 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
+            TCT_LAP(1)
             const long long blk0 = (long long)tile * TILE_BLOCKS;
             const bool interior = (blk0 + TILE_BLOCKS) * 128 <= prm.n_out;
             if (prm.flags & 2) goto epi_next;           // tuning switch: skip the global stores
+            if (interior && prm.out_bulk) {
+#pragma unroll
+                for (int r = 0; r < NSEQ; r++) {          // r = jb (complex) / j (real)
+                    if (store_thread) bulk_wait_read<kOutStages - 1>();   // the bulk store that last read this buffer is done with it
+                    epi_bar_sync();
+                    unsigned char *buf = ost_gen + obuf * kOutStageBytes;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+#pragma unroll
+                        for (int gl = 0; gl < 4; gl++) {
+                            const int gam = half * 8 + c * 4 + gl;
+                            if constexpr (COMPLEX) {
+                                reinterpret_cast<float2 *>(buf)[gam * 128 + p] =
+                                    make_float2(__uint_as_float(v[c][8 * gl + 2 * r]), __uint_as_float(v[c][8 * gl + 2 * r + 1]));
+                            } else {
+                                reinterpret_cast<float *>(buf)[gam * 128 + p] = __uint_as_float(v[c][8 * gl + r]);
+                            }
+                        }
+                    }
+                    fence_proxy_async();                  // generic-proxy writes -> visible to the bulk copy
+                    epi_bar_sync();
+                    if (store_thread)
+                        bulk_store(prm.out + ((blk0 + (long long)kAtomsOut * r) * 128) * (COMPLEX ? 2 : 1),
+                                   ost_base + obuf * kOutStageBytes, ROUND_BYTES);
+                    obuf ^= 1;
+                }
+                goto epi_next;
+            }
 #pragma unroll
             for (int c = 0; c < 2; c++) {
 #pragma unroll
@@ -507,14 +620,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                             const float2 val = make_float2(__uint_as_float(v[c][8 * gl + 2 * jb]),
                                                            __uint_as_float(v[c][8 * gl + 2 * jb + 1]));
                             if (interior || (blk0 + gam + kAtomsOut * jb) * 128 + p < prm.n_out)
-                                o[(long long)kAtomsOut * jb * 128] = val;
+                                B2S_TC_STORE(o + (long long)kAtomsOut * jb * 128, val);
                         }
                     } else {
                         float *o = prm.out + (blk0 + gam) * 128 + p;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             if (interior || (blk0 + gam + kAtomsOut * j) * 128 + p < prm.n_out)
-                                o[(long long)kAtomsOut * j * 128] = __uint_as_float(v[c][8 * gl + j]);
+                                B2S_TC_STORE(o + (long long)kAtomsOut * j * 128, __uint_as_float(v[c][8 * gl + j]));
                         }
                     }
                 }
@@ -522,6 +635,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         epi_next:
             if (++acc == nacc) { acc = 0; accphase ^= 1; }
         }
+        if (store_thread) bulk_wait_all();               // staging buffers must outlive the bulk stores
+        if (ew == 0 && lane == 0) TCT_DUMP(3, 3)
     }
 
     tc_fence_before();
@@ -574,9 +689,30 @@ int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, si
     const long long tile_items = cplx ? 64 * 128 : 128 * 128;
     prm.num_tiles = (int)ceil_div(n_out, (size_t)tile_items);
     prm.flags = f->tc_flags;
+    prm.out_bulk = (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !(f->tc_flags & 16);   // flags bit4: force per-lane stores
     const int grid = std::min(prm.num_tiles, ctx->sm_count);
     if (cplx) fir_tc_kernel<true><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
     else fir_tc_kernel<false><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
     B2S_CHECK_LAUNCH(ctx);
+#ifdef B2S_TC_TIMING
+    if (getenv("B2S_TC_TIMING_DUMP")) {
+        static int calls = 0;
+        if (++calls == 8) {                       // a warm launch
+            cudaStreamSynchronize(stream);
+            static long long h[256 * 16];
+            cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
+            const char *names[13] = {"mma.wait_full", "mma.wait_tempty", "mma.issue", "epi.wait_tfull", "epi.tmem_ld",
+                                     "epi.stores", "cvt.wait_empty", "cvt.work", "cvt.wait_rfull", "tma.wait_rempty", "tma.issue",
+                                     "mma.loop_start", "mma.loop_end"};
+            const double tiles = (double)prm.num_tiles / grid;
+            for (int i = 0; i < 13; i++) {
+                double sum = 0;
+                for (int b = 0; b < grid; b++) sum += (double)h[b * 16 + i];
+                if (i < 11) fprintf(stderr, "TCT %-16s %9.0f cycles/tile\n", names[i], sum / grid / tiles);
+                else fprintf(stderr, "TCT %-16s %9.0f cycles after kernel entry (mean over CTAs)\n", names[i], sum / grid);
+            }
+        }
+    }
+#endif
     return B2S_OK;
 }

@@ -12,7 +12,7 @@ the reference, perf/fir/fir.rs:97).
 
 The exchange is latency-bound (~tens of microseconds), so it is taken off the critical path: the
 all-gather is launched asynchronously, the outputs whose window lies entirely inside the rank's
-own chunk (all but the first ``H/D``) are computed meanwhile, and only a small second launch for
+own chunk (all but the first ``split/D``, split = H rounded up to an aligned slice) are computed meanwhile, and only a small second launch for
 the first ``H/D`` outputs waits for the neighbour's tail.
 
 The per-rank compute is the same C-ABI FIR plan as the single-GPU path; ``compute`` can be
@@ -42,7 +42,13 @@ class ShardedFir:
         self.halo = ((self.ntaps + self.decim - 2) // self.decim) * self.decim
         if self.S % self.decim:
             raise ValueError("chunk_items must be a multiple of decim so shard phases align")
-        if self.S < self.halo + self.ntaps:
+        # Split point of the overlapped step: outputs [0, split/D) need the neighbour's tail, the rest only
+        # the rank's own chunk.  It is H rounded up so that both xbuf[split:] and out[split/D:] stay 16-byte
+        # aligned -- an unaligned slice would push the FIR plan onto its scalar fallback kernel.
+        isz = np.dtype(sample_dtype).itemsize
+        q = self.decim * max(1, 16 // isz)
+        self.split = ((self.halo + q - 1) // q) * q
+        if self.S < self.split + self.ntaps:
             raise ValueError("chunk shorter than the FIR history")
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -99,13 +105,14 @@ class ShardedFir:
         elif H == 0:
             res = self.compute(self.xbuf, out)
         elif self.overlap:
-            nh = H // D                                                  # outputs that need the neighbour's tail
-            c1, p1, st = self.compute(self.xbuf[H:], out[nh:])           # windows fully inside the own chunk
+            A = self.split
+            nh = A // D                                                  # outputs that (may) need the neighbour's tail
+            c1, p1, st = self.compute(self.xbuf[A:], out[nh:])           # windows fully inside the own chunk
             if work is not None:
                 work.wait()
                 work = None
             self.xbuf[:H].copy_(self.tails[self.rank - 1][:H])
-            c0, p0, _ = self.compute(self.xbuf[:H + N - 1], out[:nh])    # the first H/D outputs
+            c0, p0, _ = self.compute(self.xbuf[:A + N - 1], out[:nh])    # the first split/D outputs
             res = (c0 + c1, p0 + p1, st)
         else:
             if work is not None:

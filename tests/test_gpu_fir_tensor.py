@@ -105,3 +105,24 @@ def test_tensor_vs_direct_full_chunk(fb):
     assert fd.filter(x, yd)[:2] == (n, n)
     scale = float(np.sum(np.abs(taps))) * float(x.abs().max())
     assert float((yt - yd).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_tensor_fir_unaligned_output_and_input(fb, rng, cplx):
+    """Outputs that are not 16-byte aligned leave through the per-lane store epilogue instead of the bulk
+    (TMA) stores; inputs that are not 16-byte aligned cannot be bulk-copied at all and take the CUDA-core
+    kernel.  Both must still match the oracle."""
+    import torch
+    ntaps, n = 200, 9 * 8192 + 1234
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    x = _noise(rng, n + 1, cplx)
+    f = fb.FirFilter(taps, sample_dtype=x.dtype, algo=fb.ALGO_TENSOR)
+    tol = 1e-5 * float(np.sum(np.abs(taps))) * float(np.max(np.abs(x)))
+    xd = torch.from_numpy(x).cuda()
+    for in_off, out_off in ((0, 1), (1, 0), (1, 1)):
+        yd = torch.zeros(n + 1, dtype=xd.dtype, device="cuda")
+        c, p, st = f.filter(xd[in_off:in_off + n], yd[out_off:out_off + n])
+        c0, p0, s0, ref = orc.fir(taps, x[in_off:in_off + n], n)
+        assert (c, p, int(st)) == (c0, p0, s0)
+        assert np.max(np.abs(yd[out_off:out_off + p].cpu().numpy() - ref)) <= tol
+        assert float(yd[out_off + p:].abs().max()) == 0.0 and (out_off == 0 or float(yd[0].abs()) == 0.0)
