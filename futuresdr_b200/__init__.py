@@ -17,3 +17,4 @@ from .filters import (  # noqa: F401
     ComputationStatus, FirFilter, DecimatingFirFilter, PolyphaseResamplingFir,
 )
 from . import firdes  # noqa: F401
+# host edges (VectorSource/Sink, FileSource/Sink, H2D/D2H ring, run_chain): futuresdr_b200.edges
