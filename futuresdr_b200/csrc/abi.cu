@@ -132,9 +132,10 @@ int32_t b2s_memcpy_d2h(b2s_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
 /* ------------------------------------------------------------------------------------------
  * FIR
  * ---------------------------------------------------------------------------------------- */
-// Below ~48 real taps the CUDA-core kernel is already HBM-bound; above it the tcgen05 kernel wins
-// (measured on B200, profiles/).
-static constexpr size_t kTensorMinTaps = 48;
+// Crossover measured on B200 (profiles/bench_configs_r1.jsonl, 64 Mi c32 samples): 16 taps direct 0.237 ms /
+// tensor 0.227 ms, 32 taps 0.290 / 0.226, 64 taps 0.423 / 0.230.  Below ~24 taps the CUDA-core kernel is
+// HBM-bound as well and keeps plain FP32 products, so it stays the default there.
+static constexpr size_t kTensorMinTaps = 24;
 // Long filters (beyond the tensor kernel's 257 taps) go to the overlap-save FFT kernel.
 static constexpr size_t kFftMinTaps = 258;
 static void resolve_algo(b2s_fir *f) {
