@@ -20,11 +20,37 @@ namespace {
 
 // arg(v * conj(last)) with num_complex's Mul: re = a.re*b.re - a.im*b.im, im = a.re*b.im + a.im*b.re,
 // b = conj(last) = (lr, -li).  __fmul_rn/__fsub_rn keep the products un-fused like the Rust code.
+// atan2 for finite inputs in ~25 instructions (CUDA's atan2f is ~60 on its fast path and made the
+// demodulator issue-bound at half the HBM roofline): a = min/max of the magnitudes (MUFU.RCP based
+// division), atan(a) = a * P(a^2) with a degree-8 minimax P (max error 1.1e-7 rad on [0,1] in f32 Horner
+// form, coefficients fitted in scripts -- see DESIGN.md 4.6), then the octant is unfolded with the SIGN
+// BITS so that +-0 behave like libm: atan2(+0,-0) = pi, atan2(0,+0) = 0 (the demodulator's first
+// sample multiplies by conj(0)).  Total error < 3e-7 rad; parity bar 1e-5*pi (tests/test_gpu_blocks.py).
+__device__ __forceinline__ float atan2_finite(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float s = a * a;
+    float p = 0.0029408063273876905f;
+    p = fmaf(p, s, -0.0164317823946476f);
+    p = fmaf(p, s, 0.04328067600727081f);
+    p = fmaf(p, s, -0.07554050534963608f);
+    p = fmaf(p, s, 0.10664203763008118f);
+    p = fmaf(p, s, -0.14209550619125366f);
+    p = fmaf(p, s, 0.19993355870246887f);
+    p = fmaf(p, s, -0.33333107829093933f);
+    p = fmaf(p, s, 1.0f);
+    float r = p * a;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (__float_as_int(x) < 0) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
 __device__ __forceinline__ float quad_demod_one(float2 v, float2 last) {
     const float cr = last.x, ci = -last.y;
     const float pr = __fsub_rn(__fmul_rn(v.x, cr), __fmul_rn(v.y, ci));
     const float pi = __fadd_rn(__fmul_rn(v.x, ci), __fmul_rn(v.y, cr));
-    return atan2f(pi, pr);
+    return atan2_finite(pi, pr);
 }
 
 template <int OP>

@@ -29,6 +29,12 @@ struct b2s_fir {
 int32_t fir_direct_prepare(b2s_fir *f);
 int32_t fir_direct_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                           cudaStream_t stream);
+// fir_direct.cu: rational resampler on the sliding-window machinery (called from resamp.cu)
+int     resamp_slide_upad(size_t M, size_t T);
+bool    resamp_slide_supported(size_t L, size_t M, size_t T, size_t item_bytes);
+void    resamp_slide_table(const float *taps, size_t L, size_t M, size_t T, std::vector<float> &g);
+int32_t resamp_slide_launch(b2s_ctx *ctx, b2s_kind kind, const float *d_gtab, size_t L, size_t M, size_t T,
+                            const void *d_in, size_t n_in, void *d_out, size_t n_out, cudaStream_t stream);
 // fir_tc.cu
 bool    fir_tc_supported(const b2s_fir *f);
 int32_t fir_tc_prepare(b2s_fir *f);

@@ -249,6 +249,174 @@ __global__ void fir_naive_kernel(const S *__restrict__ in, S *__restrict__ out,
     out[k] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rational resampler on the same machinery (futuredsp::PolyphaseResamplingFir,
+// polyphase_resampling_fir.rs:70-124):   o[k] = sum_t i[floor(k*M/L) + t] * taps[L*(T-1-t) + (k*M mod L)].
+// Write k = L*j + k0: outputs with the same k0 share a polyphase bank and their windows start
+// M items apart, i.e. for every k0 the resampler is a decimate-by-M FIR:
+//      o[L*j + k0] = sum_q sum_u x_q[j + u] * G[k0][q][u],     x_q[m] = i[M*m + q]
+// with G[k0][q][u] = bank_k0[M*u + q - s_k0], s_k0 = floor(k0*M/L) (host table, zero padded to a
+// multiple of R).  A CTA stages the M phase rows of its input tile ONCE, then runs the sliding
+// register-window loop of the direct FIR L times (one pass per k0) and leaves through a shared-memory
+// transpose so that global stores are contiguous 16-byte vectors.  Compared with one thread per
+// output reading every sample from shared memory (resamp.cu) this does R*R MACs per R-item segment
+// load instead of 1.6 FMA per LDS.
+// ---------------------------------------------------------------------------------------------
+template <typename S, int R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *__restrict__ gtab,
+                    int L, int M, int Upad, int pitch /*items per phase row*/, int opitch /*chunks per output row*/,
+                    long long n_in, long long n_out, int vec_ok) {
+    constexpr int EPC = 16 / sizeof(S);
+    constexpr int TK = THREADS * R;                 // j's per CTA; the CTA produces L*TK outputs
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const long long j0 = (long long)blockIdx.x * TK;
+    const int W = TK + Upad;
+    unsigned char *xs = smem;                                                    // [M][pitch] items
+    unsigned char *os = smem + (size_t)M * pitch * sizeof(S);                    // [L][opitch] 16-byte chunks
+    float *gs = reinterpret_cast<float *>(os + (size_t)L * opitch * 16);         // [L][M][Upad]
+
+    for (int i = tid; i < L * M * Upad; i += THREADS) gs[i] = gtab[i];
+
+    // ---- stage the input tile, de-interleaved into M phase rows (same scheme as the decimator)
+    const long long s0 = j0 * M;
+    const int total = M * W;
+    if (vec_ok) {
+        const int nchunks = (total + EPC - 1) / EPC;
+        constexpr int UNR = 4;
+        int q = (tid * EPC) % M, m = (tid * EPC) / M;
+        const int dq = (THREADS * EPC) % M, dm = (THREADS * EPC) / M;
+        for (int c0 = tid; c0 < nchunks; c0 += THREADS * UNR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int c = c0 + u * THREADS;
+                const long long s = s0 + (long long)c * EPC;
+                if (c < nchunks && s + EPC <= n_in) {
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(in + s));
+                } else {
+                    S tmp[EPC];
+#pragma unroll
+                    for (int e = 0; e < EPC; e++) tmp[e] = (c < nchunks && s + e < n_in) ? in[s + e] : zero_of<S>();
+                    v[u] = *reinterpret_cast<float4 *>(tmp);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int c = c0 + u * THREADS;
+                const S *items = reinterpret_cast<const S *>(&v[u]);
+                int qe = q, me = m;
+#pragma unroll
+                for (int e = 0; e < EPC; e++) {
+                    if (c < nchunks && c * EPC + e < total) {
+                        const int chunk = me / EPC, el = me % EPC;
+                        *reinterpret_cast<S *>(xs + ((size_t)qe * pitch + (swz(chunk) ^ (qe & 7)) * EPC + el) * sizeof(S)) = items[e];
+                    }
+                    if (++qe == M) { qe = 0; me++; }
+                }
+                q += dq; m += dm;
+                if (q >= M) { q -= M; m += 1; }
+            }
+        }
+    } else {
+        int q = tid % M, m = tid / M;
+        const int dq = THREADS % M, dm = THREADS / M;
+        for (int j = tid; j < total; j += THREADS) {
+            const long long s = s0 + j;
+            const S v = (s < n_in) ? in[s] : zero_of<S>();
+            const int chunk = m / EPC, e = m % EPC;
+            *reinterpret_cast<S *>(xs + ((size_t)q * pitch + (swz(chunk) ^ (q & 7)) * EPC + e) * sizeof(S)) = v;
+            q += dq; m += dm;
+            if (q >= M) { q -= M; m += 1; }
+        }
+    }
+    __syncthreads();
+
+    // ---- one sliding-window pass per k0
+    const int nchunk_taps = Upad / R;
+    for (int k0 = 0; k0 < L; k0++) {
+        S acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = zero_of<S>();
+        for (int q = 0; q < M; q++) {
+            const unsigned char *row = xs + (size_t)q * pitch * sizeof(S);
+            const float *g = gs + ((size_t)k0 * M + q) * Upad;
+            S win[2 * R];
+            {
+                S first[R];
+                load_segment<S, R>(first, row, tid, q & 7);
+#pragma unroll
+                for (int r = 0; r < R; r++) win[r] = first[r];
+            }
+            for (int c = 0; c < nchunk_taps; c++) {
+                S nxt[R];
+                load_segment<S, R>(nxt, row, tid + c + 1, q & 7);
+#pragma unroll
+                for (int r = 0; r < R; r++) win[R + r] = nxt[r];
+                float tp[R];
+                {
+                    constexpr int NV = R * sizeof(float) / 16;
+                    const float4 *gv = reinterpret_cast<const float4 *>(g + c * R);
+#pragma unroll
+                    for (int v = 0; v < NV; v++) reinterpret_cast<float4 *>(tp)[v] = gv[v];
+                }
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) mac(acc[r], win[r + j], tp[j]);
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) win[r] = win[R + r];
+            }
+        }
+        // row k0 of the output staging: this thread's R consecutive j's, swizzled 16-byte chunks
+        constexpr int CPS = R / EPC;
+        unsigned char *orow = os + (size_t)k0 * opitch * 16;
+#pragma unroll
+        for (int jj = 0; jj < CPS; jj++) {
+            float4 v;
+            if constexpr (sizeof(S) == 8) {
+                v = make_float4(acc[2 * jj].x, acc[2 * jj].y, acc[2 * jj + 1].x, acc[2 * jj + 1].y);
+            } else {
+                v = make_float4(*reinterpret_cast<float *>(&acc[4 * jj]), *reinterpret_cast<float *>(&acc[4 * jj + 1]),
+                                *reinterpret_cast<float *>(&acc[4 * jj + 2]), *reinterpret_cast<float *>(&acc[4 * jj + 3]));
+            }
+            *reinterpret_cast<float4 *>(orow + swz(tid * CPS + jj) * 16) = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- interleave the L rows back into output order: o = L*j + k0, contiguous 16-byte vector stores
+    {
+        const long long o0 = j0 * L;
+        const int nout_chunks = L * TK / EPC;                       // TK is a multiple of EPC
+        int k = (tid * EPC) % L, j = (tid * EPC) / L;
+        const int dk = (THREADS * EPC) % L, dj = (THREADS * EPC) / L;
+        for (int c = tid; c < nout_chunks; c += THREADS) {
+            const long long o = o0 + (long long)c * EPC;
+            if (o >= n_out) break;
+            S items[EPC];
+            int ke = k, je = j;
+#pragma unroll
+            for (int e = 0; e < EPC; e++) {
+                const int chunk = je / EPC, el = je % EPC;
+                items[e] = *reinterpret_cast<const S *>(os + ((size_t)ke * opitch + swz(chunk)) * 16 + el * sizeof(S));
+                if (++ke == L) { ke = 0; je++; }
+            }
+            if (vec_ok && o + EPC <= n_out) {
+                *reinterpret_cast<float4 *>(out + o) = *reinterpret_cast<float4 *>(items);
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPC; e++)
+                    if (o + e < n_out) out[o + e] = items[e];
+            }
+            k += dk; j += dj;
+            if (k >= L) { k -= L; j += 1; }
+        }
+    }
+}
+
 constexpr int kThreads = 128;
 constexpr int kR = 8;
 constexpr size_t kSmemBudget = 160 * 1024;
@@ -322,4 +490,63 @@ int32_t fir_direct_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out
         case B2S_C32_C32: return launch_typed<float2, float2>(f, d_in, n_in, d_out, n_out, stream);
     }
     return b2s_fail(f->ctx, B2S_EINVAL, "bad kind");
+}
+
+// ---- resampler entry points (used by resamp.cu) ------------------------------------------------
+namespace {
+constexpr int kRsSlideThreads = 128;
+constexpr size_t kRsSlideSmemMax = 96 * 1024;        // keep >= 2 CTAs per SM
+size_t resamp_slide_smem(size_t L, size_t M, size_t Upad, size_t isz) {
+    const size_t TK = (size_t)kRsSlideThreads * kR, EPC = 16 / isz;
+    const size_t pitch = round_up(TK + Upad, 8 * EPC), opitch = TK / EPC + 1;
+    return M * pitch * isz + L * opitch * 16 + L * M * Upad * sizeof(float);
+}
+}  // namespace
+
+int resamp_slide_upad(size_t M, size_t T) { return (int)round_up((T + M - 2) / M + 1, (size_t)kR); }
+
+bool resamp_slide_supported(size_t L, size_t M, size_t T, size_t item_bytes) {
+    const size_t Upad = (size_t)resamp_slide_upad(M, T);
+    // worthwhile only while the zero padding of the per-phase taps stays small (T/M taps per phase row)
+    if (Upad * M > 2 * (T + M) + 16) return false;
+    return resamp_slide_smem(L, M, Upad, item_bytes) <= kRsSlideSmemMax;
+}
+
+// G[k0][q][u] = bank_k0[M*u + q - s_k0],  bank_k0[t] = taps[L*(T-1-t) + (k0*M mod L)],  s_k0 = floor(k0*M/L)
+void resamp_slide_table(const float *taps, size_t L, size_t M, size_t T, std::vector<float> &g) {
+    const size_t Upad = (size_t)resamp_slide_upad(M, T);
+    g.assign(L * M * Upad, 0.0f);
+    for (size_t k0 = 0; k0 < L; k0++) {
+        const size_t bank = (k0 * M) % L, s = (k0 * M) / L;
+        for (size_t q = 0; q < M; q++)
+            for (size_t u = 0; u < Upad; u++) {
+                const long long t = (long long)(M * u + q) - (long long)s;
+                if (t < 0 || t >= (long long)T) continue;
+                g[(k0 * M + q) * Upad + u] = taps[L * (T - 1 - (size_t)t) + bank];
+            }
+    }
+}
+
+int32_t resamp_slide_launch(b2s_ctx *ctx, b2s_kind kind, const float *d_gtab, size_t L, size_t M, size_t T,
+                            const void *d_in, size_t n_in, void *d_out, size_t n_out, cudaStream_t stream) {
+    const size_t isz = kind_in_bytes(kind), EPC = 16 / isz;
+    const size_t Upad = (size_t)resamp_slide_upad(M, T);
+    const size_t TK = (size_t)kRsSlideThreads * kR;
+    const int pitch = (int)round_up(TK + Upad, 8 * EPC), opitch = (int)(TK / EPC + 1);
+    const size_t smem = resamp_slide_smem(L, M, Upad, isz);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    const unsigned grid = (unsigned)ceil_div(n_out, L * TK);
+    if (kind == B2S_F32_F32) {
+        auto kern = resamp_slide_kernel<float, kR, kRsSlideThreads>;
+        B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
+        kern<<<grid, kRsSlideThreads, smem, stream>>>((const float *)d_in, (float *)d_out, d_gtab, (int)L, (int)M, (int)Upad,
+                                                      pitch, opitch, (long long)n_in, (long long)n_out, vec_ok);
+    } else {
+        auto kern = resamp_slide_kernel<float2, kR, kRsSlideThreads>;
+        B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
+        kern<<<grid, kRsSlideThreads, smem, stream>>>((const float2 *)d_in, (float2 *)d_out, d_gtab, (int)L, (int)M, (int)Upad,
+                                                      pitch, opitch, (long long)n_in, (long long)n_out, vec_ok);
+    }
+    B2S_CHECK_LAUNCH(ctx);
+    return B2S_OK;
 }

@@ -8,7 +8,7 @@
 // A CTA produces TK consecutive outputs: it stages the contiguous input span those outputs
 // touch plus the bank table in shared memory, then each thread walks its outputs' T taps.
 // The (consumed, produced, status) triple follows :92-106 exactly (produced is a multiple of L).
-#include "common.cuh"
+#include "fir.cuh"
 
 struct b2s_resamp {
     b2s_ctx *ctx = nullptr;
@@ -16,6 +16,7 @@ struct b2s_resamp {
     size_t ntaps = 0, interp = 1, decim = 1, T = 0;
     int pitch = 0;
     float *d_banks = nullptr;    // [L][pitch]
+    float *d_gtab = nullptr;     // [L][M][Upad] per-phase taps of the sliding-window kernel (fir_direct.cu), or NULL
 };
 
 namespace {
@@ -106,6 +107,13 @@ int32_t b2s_resamp_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t n
     cudaError_t e = cudaMalloc((void **)&r->d_banks, h.size() * sizeof(float));
     if (e != cudaSuccess) { delete r; return b2s_fail(ctx, B2S_ENOMEM, "resampler taps"); }
     B2S_CUDA(ctx, cudaMemcpyAsync(r->d_banks, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float> gt;
+    if (resamp_slide_supported(interp, decim, r->T, kind_in_bytes(kind)) && !getenv("B2S_RESAMP_NO_SLIDE")) {
+        resamp_slide_table(taps, interp, decim, r->T, gt);
+        e = cudaMalloc((void **)&r->d_gtab, gt.size() * sizeof(float));
+        if (e != cudaSuccess) { cudaFree(r->d_banks); delete r; return b2s_fail(ctx, B2S_ENOMEM, "resampler phase taps"); }
+        B2S_CUDA(ctx, cudaMemcpyAsync(r->d_gtab, gt.data(), gt.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = r;
     return B2S_OK;
@@ -116,6 +124,7 @@ void b2s_resamp_destroy(b2s_resamp *r) {
     DeviceGuard g(r->ctx->device);
     cudaStreamSynchronize(r->ctx->stream);
     if (r->d_banks) cudaFree(r->d_banks);
+    if (r->d_gtab) cudaFree(r->d_gtab);
     delete r;
 }
 
@@ -136,6 +145,8 @@ int32_t b2s_resamp_exec(b2s_resamp *r, const void *d_in, size_t n_in, void *d_ou
     if (p == 0) return B2S_OK;
     if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_resamp_exec: NULL buffer");
     DeviceGuard g(ctx->device);
+    if (r->d_gtab)   // small L*M: L decimate-by-M sliding-window passes over one staged tile (fir_direct.cu)
+        return resamp_slide_launch(ctx, r->kind, r->d_gtab, L, M, T, d_in, n_in, d_out, p, ctx->stream);
     const size_t isz = kind_in_bytes(r->kind);
     const int G = (int)ceil_div((size_t)kRsThreads, L);                      // S = L*G >= 256 outputs per slab
     const size_t tile_out = (size_t)kRsR * L * G;

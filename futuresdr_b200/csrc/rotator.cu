@@ -98,12 +98,13 @@ int32_t b2s_rotator_exec(b2s_rotator *r, const void *d_in, size_t n_in, void *d_
         B2S_CUDA(ctx, cudaMalloc((void **)&r->d_recs, r->recs_cap * sizeof(float2)));
         B2S_CUDA(ctx, cudaHostAlloc((void **)&r->h_recs, r->recs_cap * sizeof(float2), cudaHostAllocDefault));
     }
-    // host replay of the recurrence (volatile: every product/sum rounded to f32, no FMA)
-    volatile float pr = r->phase[0], pi = r->phase[1];
+    // host replay of the recurrence: plain binary32 SSE operations (host code is built with
+    // -ffp-contract=off and without -ffast-math, so every product and sum is rounded separately)
+    float pr = r->phase[0], pi = r->phase[1];
     const float ir = r->incr[0], ii = r->incr[1];
     for (size_t s = 0; s < n; s++) {
         if ((s % kRotSub) == 0) r->h_recs[s / kRotSub] = make_float2(pr, pi);
-        volatile float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;
+        const float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;
         const float nr = a - b, ni = c + d;
         pr = nr; pi = ni;
     }

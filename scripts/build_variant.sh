@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../futuresdr_b200/csrc"
 NAME=$1; EXTRA=$2
 mkdir -p ../variants build_$NAME
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ -I../../include -I. --expt-relaxed-constexpr $EXTRA"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -ffp-contract=off -ccbin /usr/bin/g++ -I../../include -I. --expt-relaxed-constexpr $EXTRA"
 OBJS=""
 for f in abi fir_direct fir_tc fir_fft firdes fft apply resamp pfbarb rotator chan synth mavg ring; do
   /usr/local/cuda/bin/nvcc $FLAGS -c $f.cu -o build_$NAME/$f.o &
