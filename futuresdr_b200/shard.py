@@ -26,6 +26,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
 
 class ShardedFir:
     def __init__(self, taps, chunk_items: int, sample_dtype=np.complex64, decim: int = 1,
@@ -67,7 +69,14 @@ class ShardedFir:
             from .filters import DecimatingFirFilter
             self._filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, algo=algo)
             compute = self._filter.filter
+            # the split/D outputs behind the exchange are a few hundred items: the CUDA-core kernel has no
+            # TMEM / tap-table prologue, so that second launch costs ~half of a tensor-kernel launch
+            self._head_filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, algo=_lib.ALGO_DIRECT)
+            head_compute = self._head_filter.filter
+        else:
+            head_compute = compute
         self.compute = compute
+        self.head_compute = head_compute
 
     @property
     def chunk(self) -> torch.Tensor:
@@ -78,13 +87,13 @@ class ShardedFir:
         """All-gather of the overlap region (every rank's last H samples). Returns a work handle or None."""
         if self.halo == 0:
             return None
-        self.my_tail.copy_(self.xbuf[self.S:])           # last `halo` samples of [halo|chunk]
+        my_tail = self.xbuf[self.S:]                     # last `halo` samples of [halo|chunk], contiguous
         if self.world == 1:
-            self.tails[0].copy_(self.my_tail)
+            self.tails[0].copy_(my_tail)
             return None
         # complex tensors travel as their (re, im) float view
         real = (lambda t: torch.view_as_real(t) if t.is_complex() else t)
-        return dist.all_gather_into_tensor(real(self.tails).reshape(-1), real(self.my_tail).reshape(-1),
+        return dist.all_gather_into_tensor(real(self.tails).reshape(-1), real(my_tail).reshape(-1),
                                            group=self.group, async_op=async_op)
 
     def step(self, out: torch.Tensor):
@@ -112,7 +121,7 @@ class ShardedFir:
                 work.wait()
                 work = None
             self.xbuf[:H].copy_(self.tails[self.rank - 1][:H])
-            c0, p0, _ = self.compute(self.xbuf[:A + N - 1], out[:nh])    # the first split/D outputs
+            c0, p0, _ = self.head_compute(self.xbuf[:A + N - 1], out[:nh])   # the first split/D outputs
             res = (c0 + c1, p0 + p1, st)
         else:
             if work is not None:
