@@ -22,7 +22,9 @@
 struct b2s_chan {
     b2s_ctx *ctx = nullptr;
     size_t N = 0, D = 0, T = 0;
-    float *d_arms = nullptr;        // [N][T]: arm_i[j] = taps[i + j*N] (utilities.rs order; newest sample <-> j = 0)
+    float *d_arms = nullptr;        // [T][N] (tap-major): d_arms[j*N + i] = arm_i[j] = taps[i + j*N] (utilities.rs:9-19;
+                                    // newest sample <-> j = 0).  Tap-major so that adjacent windows -- which meet
+                                    // adjacent arms -- read adjacent floats (arm-major cost 32 L1 lines per warp load)
     float2 *d_circ = nullptr;       // [N][2T] circular windows (used while filling)
     float2 *d_hist = nullptr;       // [N][T] windows in time order once filled
     int *d_wstate = nullptr;        // [2N]: start_idx[N], missing[N]
@@ -66,29 +68,56 @@ __device__ __forceinline__ float2 chan_sample(const float2 *__restrict__ in, con
     return hist[(size_t)b * T + (T - 1 - (j - m))];
 }
 
+// One thread per window b, walking a run of consecutive output vectors: everything that depends on the
+// output index (newest push of the window, how many of its T samples come from this call, which arm the
+// window meets) is advanced with adds and compares instead of the six 64-bit divisions per output the
+// first version spent -- they, not the 2*T FMAs, were the cost of this kernel.  Loads are coalesced across
+// b (adjacent windows receive adjacent input samples); the T-sample reuse between consecutive outputs of a
+// thread is served by L1.  The MAC order is the reference's (oldest sample first, channelizer.rs:186-199).
 __global__ void chan_bank_kernel(const float2 *__restrict__ in, const float2 *__restrict__ hist,
                                  const float *__restrict__ arms, float2 *__restrict__ fftbuf, int N, int D, int T,
-                                 int base0, long long nprod) {
-    const long long total = nprod * N;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
-        const long long o = g / N;
-        const int b = (int)(g % N);                                    // window / fft_buf index
-        const long long E = (o + 1) * D;                               // pushes done when output o is formed
-        const int r = ((base0 - b) % N + N) % N;                        // this window receives c == r (mod N)
-        long long c_new = -1; int m = 0;
-        if (E - 1 >= r) { c_new = r + ((E - 1 - r) / N) * N; m = (int)((c_new - r) / N) + 1; }
-        const int base_after = (int)(((base0 - E) % N + N) % N);
-        const int i = ((b - base_after - 1) % N + N) % N;               // arm: b = (base_after + i + 1) % N
-        const float *a = arms + (size_t)i * T;
+                                 int base0, long long nprod, int orun) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;               // window / fft_buf index
+    if (b >= N) return;
+    const long long o_begin = (long long)blockIdx.y * orun;
+    const long long o_end = min(o_begin + (long long)orun, nprod);
+    if (o_begin >= o_end) return;
+    const int r = ((base0 - b) % N + N) % N;                           // this window receives pushes c == r (mod N)
+    // closed forms at the first output of the run
+    long long E = (o_begin + 1) * D;                                   // pushes done when output o is formed
+    long long c_new = -1; int m = 0;
+    if (E - 1 >= r) { c_new = r + ((E - 1 - r) / N) * N; m = (int)((c_new - r) / N) + 1; }
+    int base_after = (int)(((base0 - E) % N + N) % N);
+    const float2 *hb = hist + (size_t)b * T;
+    for (long long o = o_begin; o < o_end; o++) {
+        int i = b - base_after - 1;                                    // arm: b = (base_after + i + 1) % N
+        if (i < 0) i += N;
+        const float *a = arms + i;                                     // arm i, tap j at a[j * N]
         float re = 0.f, im = 0.f;
         // reference order: t = 0 (oldest) .. T-1 with tap arm[T-1-t]  <=>  j = T-1 .. 0 with tap arm[j]
-        for (int j = T - 1; j >= 0; j--) {
-            const float2 x = chan_sample(in, hist, T, N, c_new, m, b, j);
-            const float tap = a[j];
-            re = fmaf(x.x, tap, re); im = fmaf(x.y, tap, im);
+        if (m >= T) {                                                  // steady state: all T samples are in this call's input
+            const float2 *xp = in + (c_new - (long long)(T - 1) * N);    // oldest sample first
+            const float *ap = a + (size_t)(T - 1) * N;
+#pragma unroll 4
+            for (int j = 0; j < T; j++, xp += N, ap -= N) {
+                const float2 v = __ldg(xp);
+                const float tap = __ldg(ap);
+                re = fmaf(v.x, tap, re); im = fmaf(v.y, tap, im);
+            }
+        } else {
+            for (int j = T - 1; j >= 0; j--) {
+                const float2 v = (j < m) ? __ldg(in + (c_new - (long long)j * N)) : hb[T - 1 - (j - m)];
+                const float tap = __ldg(a + (size_t)j * N);
+                re = fmaf(v.x, tap, re); im = fmaf(v.y, tap, im);
+            }
         }
-        fftbuf[g] = make_float2(re, im);
+        fftbuf[o * N + b] = make_float2(re, im);
+        // advance to output o + 1:  E += D (D <= N, so the window gains at most one sample)
+        E += D;
+        if (c_new < 0) { if (E - 1 >= r) { c_new = r; m = 1; } }
+        else if (c_new + N <= E - 1) { c_new += N; m++; }
+        base_after -= D;
+        if (base_after < 0) base_after += N;
     }
 }
 
@@ -145,7 +174,7 @@ int32_t b2s_chan_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps, 
     const size_t N = c->N, T = (size_t)std::ceil((float)ntaps / (float)N);       // utilities.rs:9
     c->T = T;
     std::vector<float> arms(N * T, 0.0f);
-    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) arms[i * T + j++] = taps[idx]; }
+    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) arms[(j++) * N + i] = taps[idx]; }
     c->start_idx.assign(N, 0); c->missing.assign(N, (int)T);
     c->base_index = N - 1;
     int32_t rc = b2s_fft_plan_c32(ctx, N, 1, 0, 0, 1.0f, &c->ifft);              // plan_fft(n, Inverse) (:114)
@@ -230,9 +259,16 @@ int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, s
         if (e != cudaSuccess) { c->d_tmp = nullptr; c->tmp_items = 0; cudaGetLastError(); return b2s_fail(ctx, B2S_ENOMEM, "channelizer workspace"); }
     }
     float2 *bank = c->d_tmp, *spec = c->d_tmp + c->tmp_items;
-    const int th = 256;
-    const unsigned grid = (unsigned)std::min<size_t>(ceil_div(items, (size_t)th), (size_t)ctx->sm_count * 32);
-    chan_bank_kernel<<<grid, th, 0, ctx->stream>>>(in, c->d_hist, c->d_arms, bank, N, D, T, (int)c->base_index, (long long)nprod);
+    {
+        const int th = (int)std::min<size_t>(128, round_up(N, 32));
+        const unsigned gx = (unsigned)ceil_div(N, (size_t)th);
+        // runs of outputs per thread: enough CTAs to fill the machine (~16 per SM), at least 32 outputs per run
+        const size_t want_y = std::max<size_t>(1, (size_t)ctx->sm_count * 16 / gx);
+        const size_t orun = std::max<size_t>(32, ceil_div(nprod, want_y));
+        dim3 grid(gx, (unsigned)ceil_div(nprod, orun));
+        chan_bank_kernel<<<grid, th, 0, ctx->stream>>>(in, c->d_hist, c->d_arms, bank, N, D, T, (int)c->base_index,
+                                                       (long long)nprod, (int)orun);
+    }
     B2S_CHECK_LAUNCH(ctx);
     size_t fc = 0, fp = 0;
     int32_t rc = b2s_fft_exec(c->ifft, bank, items, spec, items, &fc, &fp);

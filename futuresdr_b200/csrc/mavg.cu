@@ -22,25 +22,86 @@ struct b2s_mavg {
 
 namespace {
 
-__global__ void mavg_kernel(const float *__restrict__ in, float *__restrict__ out, float *avg, int width,
-                            long long nchunks, int history, int i0, float decay, long long max_out) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= width) return;
-    float a = avg[b];
+// A CTA owns 32 bins.  The recurrence itself is 2 dependent operations per chunk in ONE lane per bin
+// (warp 0), which cannot keep HBM busy on its own, so all 8 warps stream blocks of 64 chunks (64 rows of
+// 128 bytes) into a 4-deep shared-memory ring with cp.async (LDGSTS: no registers held across the wait),
+// three blocks ahead of the one warp 0 is walking.  Operations and their order are the reference's
+// (un-fused IEEE mul/add).  (A register double buffer, one block ahead, spent 4 us per block waiting for
+// a single DRAM round trip: 66 ns per chunk.)
+constexpr int kMaBins = 32, kMaFrames = 64, kMaWarps = 8, kMaStages = 4;
+
+__device__ __forceinline__ void ma_cp_async4(float *dst_smem, const float *src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? 4 : 0;                        // src-size 0: the 4 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kMaWarps)
+mavg_kernel(const float *__restrict__ in, float *__restrict__ out, float *avg, int width,
+            long long nchunks, int history, int i0, float decay, long long max_out) {
+    __shared__ float buf[kMaStages][kMaFrames][kMaBins];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kMaBins + lane;
+    const bool live = b < width;
+    const long long nblk = (nchunks + kMaFrames - 1) / kMaFrames;
+    constexpr int PER = kMaFrames / kMaWarps;            // rows each warp fetches per block
+    auto issue = [&](long long blk) {                    // always commits a group, possibly empty
+        if (blk < nblk) {
+            const int stage = (int)(blk % kMaStages);
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int f = warp + k * kMaWarps;
+                const long long c = blk * kMaFrames + f;
+                const bool ok = live && c < nchunks;
+                ma_cp_async4(&buf[stage][f][lane], ok ? in + c * width + b : in, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float a = live ? avg[b] : 0.0f;
     const float keep = __fsub_rn(1.0f, decay);
     int i = i0;
     long long produced = 0;
-    for (long long c = 0; c < nchunks; c++) {
-        const float t = __ldg(in + c * width + b);
-        if (isfinite(t)) a = __fadd_rn(__fmul_rn(keep, a), __fmul_rn(decay, t));
-        else a = __fmul_rn(a, keep);
-        if (++i == history) {
-            if (produced < max_out) out[produced * width + b] = a;
-            produced++;
-            i = 0;
+    float *outp = out + (live ? b : 0);                  // next emission of this bin (only warp 0 uses it)
+    for (int s = 0; s < kMaStages - 1; s++) issue(s);
+    for (long long blk = 0; blk < nblk; blk++) {
+        issue(blk + kMaStages - 1);                      // refills the stage warp 0 finished in the previous iteration
+        asm volatile("cp.async.wait_group %0;" ::"n"(kMaStages - 1) : "memory");
+        __syncthreads();                                 // block blk has landed for every thread's copies
+        if (warp == 0 && live) {
+            const int stage = (int)(blk % kMaStages);
+            const int nf = (int)min((long long)kMaFrames, nchunks - blk * kMaFrames);
+            // One warp walks the chunks in order, so what matters is the length of the per-chunk instruction
+            // sequence: branch-free body (selects and a predicated store), loads and decay*t products hoisted
+            // out of the dependent chain, a running output pointer instead of a 64-bit multiply.
+            auto step = [&](float t, float dt) {
+                const float ka = __fmul_rn(keep, a);              // == a * keep of the non-finite branch (:89)
+                a = isfinite(t) ? __fadd_rn(ka, dt) : ka;
+                const bool emit = ++i == history;
+                if (emit && produced < max_out) *outp = a;
+                outp += emit ? width : 0;
+                produced += emit ? 1 : 0;
+                i = emit ? 0 : i;
+            };
+            if (nf == kMaFrames) {
+#pragma unroll 1
+                for (int f0 = 0; f0 < kMaFrames; f0 += 16) {
+                    float t[16], dt[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) { t[k] = buf[stage][f0 + k][lane]; dt[k] = __fmul_rn(decay, t[k]); }
+#pragma unroll
+                    for (int k = 0; k < 16; k++) step(t[k], dt[k]);
+                }
+            } else {
+                for (int f = 0; f < nf; f++) {
+                    const float t = buf[stage][f][lane];
+                    step(t, __fmul_rn(decay, t));
+                }
+            }
         }
+        __syncthreads();                                 // stage may be overwritten by the next iteration's issue
     }
-    avg[b] = a;
+    if (warp == 0 && live) avg[b] = a;
 }
 
 }  // namespace
@@ -88,8 +149,7 @@ int32_t b2s_mavg_exec(b2s_mavg *m, const void *d_in, size_t n_in, void *d_out, s
     if (c == 0) return B2S_OK;
     if (!d_in || (!d_out && p)) return b2s_fail(m->ctx, B2S_EINVAL, "b2s_mavg_exec: NULL buffer");
     DeviceGuard g(m->ctx->device);
-    const int th = 128;
-    mavg_kernel<<<(unsigned)ceil_div(W, (size_t)th), th, 0, m->ctx->stream>>>(
+    mavg_kernel<<<(unsigned)ceil_div(W, (size_t)kMaBins), 32 * kMaWarps, 0, m->ctx->stream>>>(
         (const float *)d_in, (float *)d_out, m->d_avg, (int)W, (long long)c, (int)m->history, (int)m->i, m->decay,
         (long long)p);
     B2S_CHECK_LAUNCH(m->ctx);

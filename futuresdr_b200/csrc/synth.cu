@@ -17,7 +17,7 @@
 struct b2s_synth {
     b2s_ctx *ctx = nullptr;
     size_t N = 0, T = 0;
-    float *d_arms = nullptr;        // [N][T] arm_w[j] = taps[w + j*N]; newest sample <-> j = 0
+    float *d_arms = nullptr;        // [T][N] tap-major: d_arms[j*N + w] = arm_w[j] = taps[w + j*N]; newest sample <-> j = 0
     float2 *d_circ = nullptr;       // [N][T] window positions while filling
     float2 *d_hist = nullptr;       // [N][T] FIFO order once filled
     size_t start_idx = 0, missing = 0;
@@ -74,12 +74,12 @@ __global__ void synth_bank_kernel(const float2 *__restrict__ spun /* steady vect
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
         const long long u = u0 + g / N;
         const int w = (int)(g % N);
-        const float *a = arms + (size_t)w * T;
+        const float *a = arms + w;                                // tap-major table: arm w, tap j at a[j * N] (coalesced across w)
         float re = 0.f, im = 0.f;
         for (int j = T - 1; j >= 0; j--) {                       // oldest first, like the reference's t = 0..T-1
             const long long up = u - j;
             const float2 x = up >= 0 ? __ldg(spun + up * N + w) : hist[(size_t)w * T + (T + up)];
-            const float tap = a[j];
+            const float tap = __ldg(a + (size_t)j * N);
             re = fmaf(x.x, tap, re); im = fmaf(x.y, tap, im);
         }
         out[g] = make_float2(re, im);
@@ -113,7 +113,7 @@ int32_t b2s_synth_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps,
     const size_t N = s->N, T = (size_t)std::ceil((float)ntaps / (float)N);     // utilities.rs:9
     s->T = T; s->missing = T;
     std::vector<float> arms(N * T, 0.0f);
-    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) arms[i * T + j++] = taps[idx]; }
+    for (size_t i = 0; i < N; i++) { size_t j = 0; for (size_t idx = i; idx < ntaps; idx += N) arms[(j++) * N + i] = taps[idx]; }
     int32_t rc = b2s_fft_plan_c32(ctx, N, 1, 0, 0, 1.0f, &s->ifft);            // plan_fft(n, Inverse) (synthesizer.rs:65)
     if (rc != B2S_OK) { delete s; return rc; }
     if (cudaMalloc((void **)&s->d_arms, arms.size() * sizeof(float)) != cudaSuccess ||
