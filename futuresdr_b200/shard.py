@@ -103,6 +103,15 @@ class ShardedFir:
         """
         H, D, N = self.halo, self.decim, self.ntaps
         first_of_stream = self.rank == 0 and not self.have_history
+        if self.world == 1:
+            # single rank: the history of step t+1 is the tail of step t's own chunk -- one device copy
+            # per step, no gather buffers
+            res = self.compute(self.xbuf[H:] if first_of_stream else self.xbuf, out)
+            if H:
+                self.xbuf[:H].copy_(self.xbuf[self.S:])
+            self.have_history = True
+            self.step_index += 1
+            return res
         work = self._exchange(async_op=self.overlap)
         if first_of_stream:
             res = self.compute(self.xbuf[H:], out)                       # no history: S-(ntaps-1) outputs

@@ -63,3 +63,32 @@ def test_sharded_fir_equals_single_stream(world, ntaps, decim, S):
         assert p.exitcode == 0
     same_len, same = q.get(timeout=5)
     assert same_len and same
+
+
+@pytest.mark.parametrize("ntaps,decim,S", [(256, 1, 4096), (52, 4, 4096), (1, 1, 64)])
+def test_single_rank_stream_continuity(ntaps, decim, S):
+    """world == 1 (no process group): the rank carries the tail of its own previous chunk as history with one
+    copy per step; the concatenated outputs equal the single-stream reference bit for bit."""
+    import oracle as orc
+    from futuresdr_b200.shard import ShardedFir
+    rng = np.random.default_rng(5)
+    steps = 4
+    x = (rng.standard_normal(S * steps) + 1j * rng.standard_normal(S * steps)).astype(np.complex64)
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+
+    def compute(src, out):
+        c, p, st, o = orc.decim_fir(taps, decim, src.numpy(), out.numel())
+        out[:p] = torch.from_numpy(o)
+        return c, p, st
+
+    sh = ShardedFir(taps, S, np.complex64, decim=decim, device=torch.device("cpu"), compute=compute)
+    assert sh.world == 1
+    got = []
+    for t in range(steps):
+        sh.chunk.copy_(torch.from_numpy(x[t * S:(t + 1) * S]))
+        out = torch.zeros(S // decim, dtype=torch.complex64)
+        c, p, st = sh.step(out)
+        got.append(out[:p].numpy().copy())
+    got = np.concatenate(got)
+    _, _, _, ref = orc.decim_fir(taps, decim, x, x.size)
+    assert got.size == ref.size and np.array_equal(got, ref)
