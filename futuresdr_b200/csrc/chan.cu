@@ -68,6 +68,52 @@ __device__ __forceinline__ float2 chan_sample(const float2 *__restrict__ in, con
     return hist[(size_t)b * T + (T - 1 - (j - m))];
 }
 
+// Critically sampled steady state (D == N, the window already holds T samples of this call): every output
+// pushes exactly one new sample into every window and the window keeps meeting the same arm, so the T samples
+// and the T taps live in REGISTERS; the output loop is unrolled T times so that the ring positions are static.
+// Per output: one 8-byte load, 2*T FMAs, one store (the general loop below re-reads all T samples and taps).
+// MAC order is unchanged: oldest sample first.
+template <int TT>
+__device__ __forceinline__ void chan_run_regs(const float2 *__restrict__ in, const float *__restrict__ a /*arm, tap j at a[j*N]*/,
+                                              float2 *__restrict__ fftbuf, int N, int b, long long c_new,
+                                              long long o_begin, long long o_end) {
+    float2 w[TT];                                   // slot k holds the sample of age (TT-1-k) at the start of a group
+    float tr[TT];
+#pragma unroll
+    for (int k = 0; k < TT; k++) {
+        w[k] = __ldg(in + (c_new - (long long)(TT - 1 - k) * N));
+        tr[k] = __ldg(a + (size_t)k * N);
+    }
+    // q[u]: the sample output o+u pushes for output o+u+1 -- fetched one whole group (TT outputs) ahead so that a
+    // DRAM/L2 round trip is paid once per TT outputs and overlaps TT*2*TT FMAs
+    const float2 *nxt = in + c_new + N;
+    float2 q[TT];
+#pragma unroll
+    for (int u = 0; u < TT; u++) q[u] = (o_begin + u + 1 < o_end) ? __ldg(nxt + (long long)u * N) : make_float2(0.f, 0.f);
+    for (long long o = o_begin; o < o_end; o += TT) {
+        float2 qn[TT];
+#pragma unroll
+        for (int u = 0; u < TT; u++)
+            qn[u] = (o + TT + u + 1 < o_end) ? __ldg(nxt + (long long)(TT + u) * N) : make_float2(0.f, 0.f);
+        nxt += (long long)TT * N;
+#pragma unroll
+        for (int u = 0; u < TT; u++) {
+            if (o + u < o_end) {
+                float re = 0.f, im = 0.f;
+#pragma unroll
+                for (int j = TT - 1; j >= 0; j--) {                 // j-th newest lives in slot (TT-1+u-j) mod TT
+                    const float2 v = w[(2 * TT - 1 + u - j) % TT];
+                    re = fmaf(v.x, tr[j], re); im = fmaf(v.y, tr[j], im);
+                }
+                fftbuf[(o + u) * N + b] = make_float2(re, im);
+                w[u] = q[u];                                       // overwrite the oldest (slot u) with the next push
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TT; u++) q[u] = qn[u];
+    }
+}
+
 // One thread per window b, walking a run of consecutive output vectors: everything that depends on the
 // output index (newest push of the window, how many of its T samples come from this call, which arm the
 // window meets) is advanced with adds and compares instead of the six 64-bit divisions per output the
@@ -89,6 +135,16 @@ __global__ void chan_bank_kernel(const float2 *__restrict__ in, const float2 *__
     if (E - 1 >= r) { c_new = r + ((E - 1 - r) / N) * N; m = (int)((c_new - r) / N) + 1; }
     int base_after = (int)(((base0 - E) % N + N) % N);
     const float2 *hb = hist + (size_t)b * T;
+    if (D == N && m >= T) {
+        int i = b - base_after - 1;
+        if (i < 0) i += N;
+        switch (T) {
+            case 4: chan_run_regs<4>(in, arms + i, fftbuf, N, b, c_new, o_begin, o_end); return;
+            case 8: chan_run_regs<8>(in, arms + i, fftbuf, N, b, c_new, o_begin, o_end); return;
+            case 16: chan_run_regs<16>(in, arms + i, fftbuf, N, b, c_new, o_begin, o_end); return;
+            default: break;
+        }
+    }
     for (long long o = o_begin; o < o_end; o++) {
         int i = b - base_after - 1;                                    // arm: b = (base_after + i + 1) % N
         if (i < 0) i += N;

@@ -51,7 +51,8 @@ def _drive(rng, N, ntaps, oversample, n, chunks):
 
 
 @pytest.mark.parametrize("N,ntaps,oversample", [(4, 8, 1.0), (8, 8 * 12, 1.0), (16, 16 * 8 + 5, 2.0), (6, 60, 1.0),
-                                                (64, 64 * 16, 1.0), (12, 12 * 7, 3.0)])
+                                                (64, 64 * 16, 1.0), (12, 12 * 7, 3.0),
+                                                (16, 16 * 4, 1.0), (8, 8 * 8, 1.0), (32, 32 * 16 - 3, 1.0)])
 def test_channelizer_parity(rng, N, ntaps, oversample):
     n = 40_000
     _drive(rng, N, ntaps, oversample, n, [1 << 30])              # everything offered at once
