@@ -316,6 +316,82 @@ private:
     const Instance &inst_; b2s_pfbarb *h_ = nullptr;
 };
 
+// ≙ futuredsp::Rotator (crates/futuredsp/src/rotator.rs:13-48): phase recurrence replayed bit for bit
+class Rotator {
+public:
+    Rotator(const Instance &inst, float phase_incr) : inst_(inst) { check(b2s_rotator_create(inst.get(), phase_incr, &h_), inst.get()); }
+    ~Rotator() { b2s_rotator_destroy(h_); }
+    Rotator(const Rotator &) = delete;
+    // Rotator::rotate (:32-47) on device slices; d_in == d_out is rotate_inplace (:24-29)
+    std::pair<size_t, ComputationStatus> rotate_device(const Complex32 *d_in, size_t n_in, Complex32 *d_out, size_t n_out) {
+        size_t n = 0; int32_t st = 0;
+        check(b2s_rotator_exec(h_, d_in, n_in, d_out, n_out, &n, &st), inst_.get());
+        return {n, static_cast<ComputationStatus>(st)};
+    }
+    void reset() { check(b2s_rotator_reset(h_), inst_.get()); }
+private:
+    const Instance &inst_; b2s_rotator *h_ = nullptr;
+};
+
+// ≙ blocks::XlatingFir (src/blocks/xlating_fir.rs:22-126): band-pass complex taps (:80-86), decimating FIR,
+// Rotator at the output rate (:97-99, :118)
+class XlatingFir {
+public:
+    XlatingFir(const Instance &inst, size_t decimation, float offset, float sample_rate)          // XlatingFir::new (:42-48)
+        : XlatingFir(inst, default_taps(decimation), decimation, offset, sample_rate) {}
+    XlatingFir(const Instance &inst, const std::vector<float> &taps, size_t decimation, float offset, float sample_rate)
+        : input(inst), output(inst), inst_(inst) {
+        if (decimation == 0) throw Error(B2S_EINVAL, "Xlating FIR: decimation must be > 0");
+        std::vector<Complex32> bpf(taps.size());
+        float incr = 0.f;
+        check(b2s_xlating_taps(taps.data(), taps.size(), offset, sample_rate, decimation,
+                               reinterpret_cast<float *>(bpf.data()), &incr));
+        filter_ = std::make_unique<DecimatingFirFilter<Complex32, Complex32>>(inst, decimation, bpf);
+        rotator_ = std::make_unique<Rotator>(inst, incr);
+    }
+    size_t n_taps() const { return filter_->length(); }
+    void work(WorkIo &io) {                                                        // xlating_fir.rs:105-126
+        auto [consumed, produced, status] = filter_->filter_device(input.slice(), input.len(), output.slice(), output.capacity());
+        if (produced) rotator_->rotate_device(output.slice(), produced, output.slice(), produced);
+        input.consume(consumed);
+        output.produce(produced);
+        if (input.finished() && status != ComputationStatus::InsufficientOutput) io.finished = true;
+    }
+    Reader<Complex32> input;
+    Writer<Complex32> output;
+private:
+    static std::vector<float> default_taps(size_t decimation) {
+        if (decimation < 2) throw Error(B2S_EINVAL, "Xlating FIR: Decimation has to be >= 2");   // :43
+        const double transition_bw = 0.1;
+        const double cutoff = std::min(0.5 - transition_bw - 2.220446049250313e-16, 1.0 / (double)decimation);
+        return firdes::kaiser::lowpass(cutoff, transition_bw, 0.0001);
+    }
+    const Instance &inst_;
+    std::unique_ptr<DecimatingFirFilter<Complex32, Complex32>> filter_;
+    std::unique_ptr<Rotator> rotator_;
+};
+
+// ≙ blocks::MovingAvg<WIDTH> (src/blocks/moving_avg.rs:24-116)
+class MovingAvg {
+public:
+    MovingAvg(const Instance &inst, size_t width, float decay_factor, size_t history_size)
+        : input(inst), output(inst), inst_(inst), width_(width) {
+        check(b2s_mavg_create(inst.get(), width, decay_factor, history_size, &h_), inst.get());   // asserts of :58-61 -> EINVAL
+    }
+    ~MovingAvg() { b2s_mavg_destroy(h_); }
+    void work(WorkIo &io) {                                                        // moving_avg.rs:72-115
+        const size_t n = input.len();
+        size_t c = 0, p = 0;
+        check(b2s_mavg_exec(h_, input.slice(), n, output.slice(), output.capacity(), &c, &p), inst_.get());
+        if (input.finished() && c / width_ == n / width_) io.finished = true;       // :106-108
+        input.consume(c); output.produce(p);
+    }
+    Reader<float> input;
+    Writer<float> output;
+private:
+    const Instance &inst_; size_t width_; b2s_mavg *h_ = nullptr;
+};
+
 // ≙ runtime::mocker::Mocker (mocker.rs:33-190): run one block without a scheduler
 template <typename Block> class Mocker {
 public:

@@ -137,6 +137,81 @@ int main() {
             CHECK(std::abs(X[4096 + k] - Complex32((float)(0.5 * std::cos(a)), (float)(0.5 * std::sin(a)))) < 1e-5f);
         }
     }
+    {   // futuredsp::Rotator (rotator.rs:23-48): out[n] = in[n] * phase_n, phase_{n+1} = phase_n * incr, un-normalised f32
+        const size_t n = 5000;
+        const float w = 0.1f;
+        std::vector<Complex32> x(n, Complex32(1.0f, -0.5f)), y(n);
+        Rotator rot(inst, w);
+        Complex32 *dx = inst.device_alloc<Complex32>(n), *dy = inst.device_alloc<Complex32>(n);
+        inst.upload(dx, x.data(), n);
+        auto r1 = rot.rotate_device(dx, 3000, dy, 3000);                 // two calls: the phase carries over
+        auto r2 = rot.rotate_device(dx + 3000, n - 3000, dy + 3000, n);
+        CHECK(r1.first == 3000 && r2.first == n - 3000);
+        inst.download(y.data(), dy, n);
+        float pr = 1.0f, pi = 0.0f;
+        const float ir = std::cos(w), ii = std::sin(w);
+        double worst = 0;
+        for (size_t k = 0; k < n; k++) {
+            const Complex32 want(x[k].real() * pr - x[k].imag() * pi, x[k].real() * pi + x[k].imag() * pr);
+            worst = std::max(worst, (double)std::abs(y[k] - want));
+            const float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;
+            pr = a - b; pi = c + d;
+        }
+        CHECK(worst <= 2e-6);
+        inst.device_free(dx); inst.device_free(dy);
+    }
+    {   // blocks::XlatingFir (xlating_fir.rs:42-126): default design, band-pass taps, decimate by 4, rotate
+        const size_t D = 4, n = 20000;
+        const float offset = 1000.0f, fs = 48000.0f;
+        XlatingFir xl(inst, D, offset, fs);
+        CHECK(xl.n_taps() == 52);
+        std::mt19937 g(3);
+        std::normal_distribution<float> nd;
+        std::vector<Complex32> x(n);
+        for (auto &v : x) v = Complex32(nd(g), nd(g));
+        Mocker m(xl);
+        m.input(x);
+        m.init_output(n / D + 4);
+        WorkIo io = m.run();
+        auto y = m.output();
+        const auto lp = firdes::kaiser::lowpass(0.25, 0.1, 0.0001);
+        const size_t nt = lp.size(), want_n = (n + 1 - nt) / D;
+        CHECK(io.finished && nt == 52 && y.size() == want_n);
+        const float TAU = 6.28318530717958647692f;
+        std::vector<Complex32> bpf(nt);
+        for (size_t i = 0; i < nt; i++) {
+            const float th = (float)i * TAU * offset / fs;
+            bpf[i] = Complex32(std::cos(th) * lp[i], std::sin(th) * lp[i]);
+        }
+        const float w = -TAU * offset * (float)D / fs;
+        Complex32 ph(1.0f, 0.0f);
+        const Complex32 inc(std::cos(w), std::sin(w));
+        double worst = 0;
+        for (size_t k = 0; k < std::min(want_n, y.size()); k++) {
+            Complex32 acc(0, 0);
+            for (size_t t = 0; t < nt; t++) acc += x[D - 1 + k * D + t] * bpf[nt - 1 - t];       // decimating_fir.rs:80-92
+            worst = std::max(worst, (double)std::abs(y[k] - acc * ph));
+            ph = ph * inc;
+        }
+        CHECK(worst <= 2e-4);
+        std::printf("XlatingFir /4: %zu outputs, worst |err| = %.3e\n", y.size(), worst);
+    }
+    {   // blocks::MovingAvg (moving_avg.rs:72-115): width 4, decay 0.5, one output chunk every 2 input chunks
+        MovingAvg ma(inst, 4, 0.5f, 2);
+        std::vector<float> in;
+        for (float v : {1.f, 3.f, 5.f, 7.f, 9.f}) for (int k = 0; k < 4; k++) in.push_back(v);
+        in.push_back(42.f);                                              // trailing partial chunk is left unconsumed
+        Mocker m(ma);
+        m.input(in);
+        m.init_output(16);
+        m.run();
+        auto v = m.output();
+        CHECK(v.size() == 8);
+        for (size_t i = 0; i < v.size() && i < 8; i++) CHECK(v[i] == (i < 4 ? 1.75f : 5.1875f));
+        bool threw = false;
+        try { MovingAvg bad(inst, 4, 1.5f, 2); } catch (const Error &) { threw = true; }
+        CHECK(threw);                                                    // assert!((0.0..=1.0).contains(&decay_factor))
+    }
     std::printf(failures ? "C++ host layer: %d FAILURES\n" : "C++ host layer: all checks passed\n", failures);
     return failures ? 1 : 0;
 }
