@@ -239,6 +239,7 @@ struct TcParams {
     int num_tiles;
     int flags;            // bit0: swap bf16 halves of the TMEM A words (bring-up switch)
     int out_bulk;         // out is 16-byte aligned: interior tiles leave through bulk (TMA) stores
+    int decim;            // D | 128: only the output phases p == D-1 (mod D) are stored (decimating FIR)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -559,7 +560,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         // unaligned outputs) kept the warps stalled on the LSU for ~40 % of a tile period.
         const int ew = warp - kEpiWarp0, q = ew & 3, half = ew >> 2, p = 32 * q + lane;
         const bool store_thread = threadIdx.x == 32 * kEpiWarp0;
-        constexpr uint32_t ROUND_BYTES = kAtomsOut * 128 * ITEM_BYTES;          // 16 blocks
+        // Decimation (decimating_fir.rs:80-92: o[k] = y[D-1 + k*D] of the full-rate FIR y): the MMAs still
+        // produce every phase -- the tensor pipe has the room, the kernel is HBM-bound below ~130 taps -- and
+        // the epilogue keeps the lanes p == D-1 (mod D).  D divides 128, so the kept lanes are the same in
+        // every block and block b contributes the 128/D outputs  k = b*(128/D) + (p-(D-1))/D.
+        const int D = prm.decim, per_blk = 128 / D;
+        const bool lane_on = (p % D) == D - 1;
+        const int pk = (p - (D - 1)) / D;
+        const uint32_t round_bytes = (uint32_t)(kAtomsOut * per_blk * ITEM_BYTES);   // 16 blocks' worth of outputs
         int acc = 0, obuf = 0;
         uint32_t accphase = 0;
         TCT_DECL(3)
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             if (lane == 0) mbar_arrive(tempty_bar(acc));     // accumulator drained -> MMA may reuse it
             TCT_LAP(1)
             const long long blk0 = (long long)tile * TILE_BLOCKS;
-            const bool interior = (blk0 + TILE_BLOCKS) * 128 <= prm.n_out;
+            const bool interior = (blk0 + TILE_BLOCKS) * per_blk <= prm.n_out;
             if (prm.flags & 2) goto epi_next;           // tuning switch: skip the global stores
             if (interior && prm.out_bulk) {
 #pragma unroll
@@ -591,19 +599,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 #pragma unroll
                         for (int gl = 0; gl < 4; gl++) {
                             const int gam = half * 8 + c * 4 + gl;
+                            if (!lane_on) continue;
                             if constexpr (COMPLEX) {
-                                reinterpret_cast<float2 *>(buf)[gam * 128 + p] =
+                                reinterpret_cast<float2 *>(buf)[gam * per_blk + pk] =
                                     make_float2(__uint_as_float(v[c][8 * gl + 2 * r]), __uint_as_float(v[c][8 * gl + 2 * r + 1]));
                             } else {
-                                reinterpret_cast<float *>(buf)[gam * 128 + p] = __uint_as_float(v[c][8 * gl + r]);
+                                reinterpret_cast<float *>(buf)[gam * per_blk + pk] = __uint_as_float(v[c][8 * gl + r]);
                             }
                         }
                     }
                     fence_proxy_async();                  // generic-proxy writes -> visible to the bulk copy
                     epi_bar_sync();
                     if (store_thread)
-                        bulk_store(prm.out + ((blk0 + (long long)kAtomsOut * r) * 128) * (COMPLEX ? 2 : 1),
-                                   ost_base + obuf * kOutStageBytes, ROUND_BYTES);
+                        bulk_store(prm.out + ((blk0 + (long long)kAtomsOut * r) * per_blk) * (COMPLEX ? 2 : 1),
+                                   ost_base + obuf * kOutStageBytes, round_bytes);
                     obuf ^= 1;
                 }
                 goto epi_next;
@@ -613,21 +622,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 #pragma unroll
                 for (int gl = 0; gl < 4; gl++) {
                     const int gam = half * 8 + c * 4 + gl;
+                    if (!lane_on) continue;
                     if constexpr (COMPLEX) {
-                        float2 *o = reinterpret_cast<float2 *>(prm.out) + (blk0 + gam) * 128 + p;
+                        float2 *o = reinterpret_cast<float2 *>(prm.out) + (blk0 + gam) * per_blk + pk;
 #pragma unroll
                         for (int jb = 0; jb < 4; jb++) {
                             const float2 val = make_float2(__uint_as_float(v[c][8 * gl + 2 * jb]),
                                                            __uint_as_float(v[c][8 * gl + 2 * jb + 1]));
-                            if (interior || (blk0 + gam + kAtomsOut * jb) * 128 + p < prm.n_out)
-                                B2S_TC_STORE(o + (long long)kAtomsOut * jb * 128, val);
+                            if (interior || (blk0 + gam + kAtomsOut * jb) * per_blk + pk < prm.n_out)
+                                B2S_TC_STORE(o + (long long)kAtomsOut * jb * per_blk, val);
                         }
                     } else {
-                        float *o = prm.out + (blk0 + gam) * 128 + p;
+                        float *o = prm.out + (blk0 + gam) * per_blk + pk;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            if (interior || (blk0 + gam + kAtomsOut * j) * 128 + p < prm.n_out)
-                                B2S_TC_STORE(o + (long long)kAtomsOut * j * 128, __uint_as_float(v[c][8 * gl + j]));
+                            if (interior || (blk0 + gam + kAtomsOut * j) * per_blk + pk < prm.n_out)
+                                B2S_TC_STORE(o + (long long)kAtomsOut * j * per_blk, __uint_as_float(v[c][8 * gl + j]));
                         }
                     }
                 }
@@ -647,7 +657,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 }  // namespace
 
 bool fir_tc_supported(const b2s_fir *f) {
-    if (f->decim != 1) return false;
+    if (f->decim == 0 || f->decim > 128 || 128 % f->decim != 0) return false;   // kept output phases must be lane-static
     if (f->kind != B2S_C32_F32 && f->kind != B2S_F32_F32) return false;
     // >= 16 taps: with fewer products the split-bf16 error (O(2^-17) per product) no longer averages
     // below the 1e-5 * ||taps||_1 * max|x| bar; short filters are HBM-bound on CUDA cores anyway.
@@ -683,11 +693,12 @@ int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, si
     prm.out = (float *)d_out;
     prm.g = f->d_ptaps + (size_t)f->decim * f->Upad;      // plain reversed taps (fir_direct_prepare)
     prm.n_in = (long long)n_in;
-    prm.n_out = (long long)n_out;
+    prm.n_out = (long long)n_out;                        // decimated count
+    prm.decim = (int)f->decim;
     prm.ntaps = (int)f->ntaps;
     prm.DK = f->tc_kblocks;
     const long long tile_items = cplx ? 64 * 128 : 128 * 128;
-    prm.num_tiles = (int)ceil_div(n_out, (size_t)tile_items);
+    prm.num_tiles = (int)ceil_div(n_out * f->decim, (size_t)tile_items);   // tiles over the full-rate index space
     prm.flags = f->tc_flags;
     prm.out_bulk = (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !(f->tc_flags & 16);   // flags bit4: force per-lane stores
     const int grid = std::min(prm.num_tiles, ctx->sm_count);

@@ -92,7 +92,11 @@ def main():
         # config 3 pieces: decimator /4 (52 taps) -> quad demod -> PfbArb 0.768
         dec = B.FirBuilder.decimating(4)
         sec = timeit(lambda: dec.filter.filter(x[:n], y[: n // 4]))
-        report("decim4_52taps_c32", n, 8 * n + 8 * (n // 4), sec)
+        report("decim4_52taps_c32", n, 8 * n + 8 * (n // 4), sec, extra=f"algo={dec.filter.algo}")
+        dtaps = fb.firdes.kaiser.lowpass(0.25, 0.1, 1e-4)
+        decd = fb.DecimatingFirFilter(4, dtaps, algo=fb.ALGO_DIRECT)
+        sec = timeit(lambda: decd.filter(x[:n], y[: n // 4]))
+        report("decim4_52taps_c32_direct", n, 8 * n + 8 * (n // 4), sec)
         n4 = n // 4
         dem = B.Apply(B.ApplyOp.QuadDemodC32)
         z = torch.empty(n4, dtype=torch.complex64, device="cuda")

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_channelizer.py tests/test_gpu_synthesizer.py -m gpu -q -x 2>&1 | tail -3
-timeout 600 python scripts/bench_configs.py --only next 2>&1 | tail -3 | cut -c1-200
+./tests/cpp/test_host 2>&1 | tail -15
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -12

@@ -137,7 +137,7 @@ int main() {
             CHECK(std::abs(X[4096 + k] - Complex32((float)(0.5 * std::cos(a)), (float)(0.5 * std::sin(a)))) < 1e-5f);
         }
     }
-    {   // futuredsp::Rotator (rotator.rs:23-48): out[n] = in[n] * phase_n, phase_{n+1} = phase_n * incr, un-normalised f32
+    {   // futuredsp::Rotator (rotator.rs:23-48): phase_n = phase_{n-1} * incr THEN out[n] = in[n] * phase_n, un-normalised f32
         const size_t n = 5000;
         const float w = 0.1f;
         std::vector<Complex32> x(n, Complex32(1.0f, -0.5f)), y(n);
@@ -152,10 +152,10 @@ int main() {
         const float ir = std::cos(w), ii = std::sin(w);
         double worst = 0;
         for (size_t k = 0; k < n; k++) {
+            const float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;     // self.phase *= self.phase_incr FIRST (:26, :40)
+            pr = a - b; pi = c + d;
             const Complex32 want(x[k].real() * pr - x[k].imag() * pi, x[k].real() * pi + x[k].imag() * pr);
             worst = std::max(worst, (double)std::abs(y[k] - want));
-            const float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;
-            pr = a - b; pi = c + d;
         }
         CHECK(worst <= 2e-6);
         inst.device_free(dx); inst.device_free(dy);
@@ -190,8 +190,8 @@ int main() {
         for (size_t k = 0; k < std::min(want_n, y.size()); k++) {
             Complex32 acc(0, 0);
             for (size_t t = 0; t < nt; t++) acc += x[D - 1 + k * D + t] * bpf[nt - 1 - t];       // decimating_fir.rs:80-92
+            ph = ph * inc;                                                       // rotator.rs:26: phase advances before use
             worst = std::max(worst, (double)std::abs(y[k] - acc * ph));
-            ph = ph * inc;
         }
         CHECK(worst <= 2e-4);
         std::printf("XlatingFir /4: %zu outputs, worst |err| = %.3e\n", y.size(), worst);

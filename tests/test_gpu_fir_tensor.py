@@ -75,8 +75,11 @@ def test_tensor_fir_kaiser_taps_and_impulse(fb, rng):
 
 
 def test_tensor_unsupported_shapes_are_refused(fb):
-    with pytest.raises(fb.B200SdrError):
-        fb.DecimatingFirFilter(2, np.ones(64, np.float32), algo=fb.ALGO_TENSOR)
+    with pytest.raises(fb.B200SdrError):       # decimation must divide 128 (the kept output phases are lane-static)
+        fb.DecimatingFirFilter(3, np.ones(64, np.float32), algo=fb.ALGO_TENSOR)
+    assert fb.DecimatingFirFilter(4, np.ones(64, np.float32), algo=fb.ALGO_TENSOR).algo == fb.ALGO_TENSOR
+    assert fb.DecimatingFirFilter(4, np.ones(52, np.float32)).algo == fb.ALGO_TENSOR      # FirBuilder::decimating(4)
+    assert fb.DecimatingFirFilter(5, np.ones(52, np.float32)).algo == fb.ALGO_DIRECT
     with pytest.raises(fb.B200SdrError):
         fb.FirFilter(np.ones(64, np.complex64), algo=fb.ALGO_TENSOR)
     with pytest.raises(fb.B200SdrError):       # < 16 taps: split-bf16 error bound too loose, refused
@@ -126,3 +129,26 @@ def test_tensor_fir_unaligned_output_and_input(fb, rng, cplx):
         assert (c, p, int(st)) == (c0, p0, s0)
         assert np.max(np.abs(yd[out_off:out_off + p].cpu().numpy() - ref)) <= tol
         assert float(yd[out_off + p:].abs().max()) == 0.0 and (out_off == 0 or float(yd[0].abs()) == 0.0)
+
+
+@pytest.mark.parametrize("decim,ntaps,cplx", [(4, 52, True), (2, 129, True), (8, 200, False), (16, 33, True),
+                                              (128, 256, True), (64, 100, False)])
+def test_tensor_decimating_fir(fb, rng, decim, ntaps, cplx):
+    """Decimating FIR on the tensor path (the epilogue keeps the output phases D-1 mod D): many interior tiles
+    (bulk stores), a ragged tail, a small output capacity, against the oracle's decimating_fir.rs restatement."""
+    import torch
+    n = 40 * 16384 + 12345
+    x = _noise(rng, n, cplx)
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    f = fb.DecimatingFirFilter(decim, taps, sample_dtype=x.dtype, algo=fb.ALGO_TENSOR)
+    assert f.algo == fb.ALGO_TENSOR
+    xd = torch.from_numpy(x).cuda()
+    tol = 1e-5 * float(np.sum(np.abs(taps))) * float(np.max(np.abs(x)))
+    for cap in (n, 1000, 1):
+        yd = torch.full((cap + 8,), 7.0, dtype=xd.dtype, device="cuda")
+        c, p, st = f.filter(xd, yd[:cap])
+        c0, p0, s0, ref = orc.decim_fir(taps, decim, x, cap)
+        assert (c, p, int(st)) == (c0, p0, s0)
+        got = yd.cpu().numpy()
+        assert np.max(np.abs(got[:p] - ref)) <= tol
+        assert np.all(got[cap:] == 7.0)                      # nothing written past the capacity
