@@ -1,7 +1,8 @@
 // fir_tc.cu -- tcgen05 (5th-gen tensor core) FIR for 16..257 real taps on sm_100a.
 //
 // Computes the same  o[k] = sum_t i[k+t] * taps[N-1-t]  as crates/futuredsp/src/fir.rs:77-88
-// (Complex<f32> or f32 samples, f32 taps, no decimation) as a block-Toeplitz GEMM:
+// (Complex<f32> or f32 samples, f32 taps; decimating_fir.rs:80-92 for a decimation D | 128: the epilogue keeps
+// the output phases D-1 mod D) as a block-Toeplitz GEMM:
 //
 //      D[p][c] = sum_kappa A[p][kappa] * B[c][kappa]            (M = 128, N = 128, K = 128*DK <= 384)
 //      A[p][kappa] = g[kappa - p]   (g[t] = taps[N-1-t], zero outside [0,N))   -- "taps, Toeplitz"

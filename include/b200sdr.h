@@ -58,7 +58,7 @@ typedef enum {
 typedef enum {
     B2S_ALGO_AUTO   = 0,
     B2S_ALGO_DIRECT = 1, /* CUDA-core register-blocked direct form (any kind, any decimation) */
-    B2S_ALGO_TENSOR = 2, /* tcgen05 block-Toeplitz GEMM, split-bf16 (real taps, 16..257, decim == 1) */
+    B2S_ALGO_TENSOR = 2, /* tcgen05 block-Toeplitz GEMM, split-bf16 (real taps, 16..257, decim divides 128) */
     B2S_ALGO_FFT    = 3  /* overlap-save FFT convolution (c32 samples, 64..2049 taps, decim == 1)  */
 } b2s_algo;
 
