@@ -38,9 +38,9 @@ class StreamBuffer:
     """Linear device buffer shared by one writer and one reader; unconsumed items are moved to the front
     when the free tail gets short (slab.rs keeps history the same way)."""
 
-    def __init__(self, dtype, capacity_items: int):
+    def __init__(self, dtype, capacity_items: int, device="cuda"):
         self.dtype = np.dtype(dtype)
-        self.data = torch.empty(int(capacity_items), dtype=_tdtype(dtype), device="cuda")
+        self.data = torch.empty(int(capacity_items), dtype=_tdtype(dtype), device=device)
         self.rd = 0
         self.wr = 0
         self.writer_finished = False
@@ -321,7 +321,7 @@ class FileSink(_HostSink):
 # ---------------------------------------------------------------------------------------------------
 # linear chain driver
 # ---------------------------------------------------------------------------------------------------
-def run_chain(stages: Sequence[Block], buffer_items: int = 4 << 20, max_rounds: int = 1 << 24):
+def run_chain(stages: Sequence[Block], buffer_items: int = 4 << 20, max_rounds: int = 1 << 24, device="cuda"):
     """Connect ``stages[0] -> stages[1] -> ...`` with device stream buffers and call ``work`` round-robin until
     the last stage reports finished.  A stage finishing marks its output stream finished, which is what the
     next stage's ``input.finished()`` reports (the reference's port ``finished`` flag, buffer/mod.rs:295-353).
@@ -331,7 +331,7 @@ def run_chain(stages: Sequence[Block], buffer_items: int = 4 << 20, max_rounds: 
     for up, down in zip(stages[:-1], stages[1:]):
         assert np.dtype(up.out_dtype) == np.dtype(down.in_dtype), \
             f"{type(up).__name__} -> {type(down).__name__}: item types differ"
-        b = StreamBuffer(up.out_dtype, buffer_items)
+        b = StreamBuffer(up.out_dtype, buffer_items, device)
         up.output, down.input = _WriterPort(b), _ReaderPort(b)
         bufs.append(b)
     done = [False] * len(stages)
@@ -355,5 +355,6 @@ def run_chain(stages: Sequence[Block], buffer_items: int = 4 << 20, max_rounds: 
             break
         if not progressed:
             raise RuntimeError("run_chain: no stage can make progress (buffer_items too small for a stage's minimum?)")
-    torch.cuda.synchronize()
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize()
     return calls
