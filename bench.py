@@ -335,6 +335,28 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        try:
+            # explanatory only: the FLOPs the tensor kernel EXECUTES (3 split-bf16 products over the block-Toeplitz
+            # operand, K = ntaps + 127 rounded up to 16) against the dense bf16 tensor peak -- at 256 taps this, not
+            # HBM, is what the kernel runs into.  The judged roofline above stays the HBM one
+            # SURVEY.md 8(d) states for this metric.
+            if fir.algo == 2:
+                ksteps = -(-(NTAPS + 127) // 16)
+                tiles = -(-CHUNK // 8192)
+                mma_flops = float(tiles) * 3 * ksteps * 2 * 128 * 128 * 16
+                tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s burst)"
+                try:
+                    mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                    if "bf16_tflops" in mp:
+                        tpeak, tsrc = float(mp["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops)"
+                except Exception:
+                    pass
+                tach = mma_flops / (k_ms * 1e-3) / 1e12
+                line["roofline"]["tensor_executed"] = {"achieved": tach, "peak": tpeak, "unit": "TFLOP/s",
+                                                       "frac": tach / tpeak, "flops_per_launch": mma_flops,
+                                                       "peak_source": tsrc}
+        except Exception:
+            pass
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
