@@ -181,3 +181,81 @@ def test_channelizer_oracle_tone_and_call_pattern(rng):
     # oversampled by 2: decimation N/2, twice the output rate
     y2 = orc.PfbChannelizer(N, taps, 2.0).run(x)
     assert y2.shape == (N, n // (N // 2))
+
+
+def test_moving_avg_oracle_vs_python_transcription(rng):
+    """MovingAvg (moving_avg.rs:72-115) has no value-pinning reference test: cross-check the C oracle bit for bit
+    against an independent numpy-f32 transcription, including non-finite inputs, the emission counter carried
+    across calls and the output-capacity stop."""
+    width, decay, history = 8, np.float32(0.3), 3
+    o = orc.MovingAvg(width, float(decay), history)
+    avg, cnt = np.zeros(width, np.float32), 0
+    one = np.float32(1.0)
+    for call, (nchunks, cap_chunks) in enumerate([(7, 10), (2, 10), (9, 1), (4, 10)]):
+        x = rng.standard_normal(nchunks * width + (call % 3)).astype(np.float32)
+        x[rng.integers(0, x.size, 3)] = [np.inf, -np.inf, np.nan]
+        want, consumed, produced = [], 0, 0
+        while (consumed + 1) * width <= x.size and (produced + 1) * width <= cap_chunks * width:
+            t = x[consumed * width:(consumed + 1) * width]
+            fin = np.isfinite(t)
+            upd = ((one - decay) * avg).astype(np.float32) + (decay * np.where(fin, t, 0)).astype(np.float32)
+            avg = np.where(fin, upd.astype(np.float32), (avg * (one - decay)).astype(np.float32)).astype(np.float32)
+            cnt += 1
+            if cnt == history:
+                want.append(avg.copy()); cnt = 0; produced += 1
+            consumed += 1
+        c, p, out = o.work(x, cap_chunks * width)
+        assert (c, p) == (consumed * width, produced * width)
+        if want:
+            assert np.array_equal(out, np.concatenate(want))
+
+
+class _PyWindow:
+    """window_buffer.rs:4-44, transcribed independently of the C oracle."""
+
+    def __init__(self, n):
+        self.n, self.buf, self.start, self.missing = n, np.zeros(2 * n, np.complex64), 0, n
+
+    def push(self, s):
+        idx = (self.start - self.missing) % self.n
+        self.buf[idx] = s
+        self.buf[idx + self.n] = s
+        self.missing = max(self.missing - 1, 0)
+        self.start = (self.start + 1) % self.n
+
+    def filled(self):
+        return self.missing == 0
+
+    def window(self):
+        return self.buf[self.start:self.start + self.n]
+
+
+def test_synthesizer_oracle_vs_python_transcription(rng):
+    """PfbSynthesizer (synthesizer.rs:80-144) has no value-pinning reference test: compare the C oracle with an
+    independent Python transcription (numpy inverse FFT instead of rustfft, hence a tolerance, not bit equality),
+    over several work() calls with different input lengths and output capacities."""
+    N, ntaps = 6, 6 * 5 + 2
+    taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
+    T = int(np.ceil(np.float32(ntaps) / np.float32(N)))
+    arms = [np.concatenate([taps[i::N], np.zeros(T - taps[i::N].size, np.float32)]) for i in range(N)]   # utilities.rs:9-19
+    wins = [_PyWindow(T) for _ in range(N)]
+    all_filled = False
+    o = orc.PfbSynthesizer(N, taps)
+    for n_in, cap in [(3, 100), (4, 100), (10, 17), (10, 6), (25, 1000)]:
+        x = (rng.standard_normal((N, n_in)) + 1j * rng.standard_normal((N, n_in))).astype(np.complex64)
+        want, consumed, produced = [], 0, 0
+        while n_in - consumed > 0 and (cap - produced > N or not all_filled):              # synthesizer.rs:92-94
+            spun = np.fft.ifft(x[:, consumed].astype(np.complex128)) * N                  # un-normalised inverse FFT
+            consumed += 1
+            for w, arm, s in zip(wins, arms, spun.astype(np.complex64)):
+                w.push(s)
+                if w.filled():
+                    win = w.window()
+                    want.append(np.sum(win.astype(np.complex128) * arm[::-1]))            # FirFilter: taps applied reversed
+                    produced += 1
+            if not all_filled:
+                all_filled = all(w.filled() for w in wins)
+        c, p, out = o.work(x, cap)
+        assert (c, p) == (consumed, produced)
+        if want:
+            assert np.max(np.abs(out - np.asarray(want))) <= 1e-4 * (np.max(np.abs(taps)) * T * N * np.max(np.abs(x)))
