@@ -50,7 +50,7 @@ def _worker(rank, world, port, ntaps, decim, S, steps, q):
 
 
 @pytest.mark.parametrize("world,ntaps,decim,S", [(2, 256, 1, 4096), (2, 52, 4, 4096), (3, 33, 3, 3000),
-                                                  (2, 1, 1, 64)])
+                                                  (2, 1, 1, 64), (4, 64, 2, 2048)])
 def test_sharded_fir_equals_single_stream(world, ntaps, decim, S):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
