@@ -226,11 +226,16 @@ def run_ours(args):
 
     taps = _taps()
     algo = {"auto": fb.ALGO_AUTO, "direct": fb.ALGO_DIRECT, "tensor": fb.ALGO_TENSOR}[args.algo]
-    sh = ShardedFir(taps, CHUNK, np.complex64, device=dev, algo=algo)
+    sh = ShardedFir(taps, CHUNK, np.complex64, device=dev, algo=algo, exchange=args.exchange)
     ctx = sh._filter.ctx
-    # synthetic white noise generated on the device (Philox), per-rank subsequence
+    # synthetic white noise generated on the device (Philox), per-rank subsequence; every ring slot is filled
+    # before the timed region (inputs resident in HBM when it starts)
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
-    torch.view_as_real(sh.chunk).normal_(generator=g)
+    if sh.exchange == "peer":
+        for tns in sh.slot_tensors():
+            torch.view_as_real(tns).normal_(generator=g)
+    else:
+        torch.view_as_real(sh.chunk).normal_(generator=g)
     out = torch.empty(CHUNK, dtype=torch.complex64, device=dev)
 
     def barrier():
@@ -251,17 +256,22 @@ def run_ours(args):
     ev[0].record()
     produced = 0
     for i in range(args.steps):
-        # the FIR kernel alone (for the roofline): events on the launching stream around compute
-        orig = sh.compute
+        # the FIR kernel alone (for the roofline): events on the launching stream around the launch
+        if sh.exchange == "peer":
+            sh.on_kernel = lambda tag, _i=i: kev[_i][0 if tag == "begin" else 1].record()
+            c, p, st = sh.step(out)
+            sh.on_kernel = None
+        else:
+            orig = sh.compute
 
-        def timed(src, o, _i=i, _f=orig):
-            kev[_i][0].record()
-            r = _f(src, o)
-            kev[_i][1].record()
-            return r
-        sh.compute = timed
-        c, p, st = sh.step(out)
-        sh.compute = orig
+            def timed(src, o, _i=i, _f=orig):
+                kev[_i][0].record()
+                r = _f(src, o)
+                kev[_i][1].record()
+                return r
+            sh.compute = timed
+            c, p, st = sh.step(out)
+            sh.compute = orig
         produced += p
         ev[i + 1].record()
     barrier()
@@ -371,6 +381,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "direct", "tensor"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="halo exchange of the sharded stream: in-kernel peer fetch over NVLink (default) or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

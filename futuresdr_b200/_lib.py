@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B2S_LIB lets a developer A/B a differently-built library (kernel tuning); default is the in-tree build
 SO_PATH = os.environ.get("B2S_LIB") or os.path.join(_HERE, "libb200sdr.so")
 
-OK, EINVAL, ECUDA, ENOMEM, EAGAIN, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6
+OK, EINVAL, ECUDA, ENOMEM, EAGAIN, EUNSUPPORTED, ESTATE, ETIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7
 INSUFFICIENT_INPUT, INSUFFICIENT_OUTPUT, BOTH_SUFFICIENT = 0, 1, 2
 F32_F32, C32_F32, C32_C32 = 0, 1, 2
 ALGO_AUTO, ALGO_DIRECT, ALGO_TENSOR, ALGO_FFT = 0, 1, 2, 3
@@ -50,6 +50,7 @@ SIGNATURES = {
     "b2s_fir_get_algo": (_i32, [_vp]),
     "b2s_fir_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp, _i32p]),
     "b2s_fir_filter_host": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp, _i32p]),
+    "b2s_fir_exec_hist": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, C.c_uint32, _vp, C.c_uint32, _szp, _szp, _i32p]),
     "b2s_resamp_plan": (_i32, [_vp, C.c_int, _f32p, _sz, _sz, _sz, _vpp]),
     "b2s_resamp_destroy": (None, [_vp]),
     "b2s_resamp_length": (_sz, [_vp]),
@@ -81,6 +82,10 @@ SIGNATURES = {
     "b2s_mavg_create": (_i32, [_vp, _sz, _f32, _sz, _vpp]),
     "b2s_mavg_destroy": (None, [_vp]),
     "b2s_mavg_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp]),
+    "b2s_spectrum_plan": (_i32, [_vp, _sz, _i32, _f32, _sz, _f32, _vpp]),
+    "b2s_spectrum_destroy": (None, [_vp]),
+    "b2s_spectrum_reset": (_i32, [_vp]),
+    "b2s_spectrum_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp]),
     "b2s_ring_create": (_i32, [_vp, _sz, _sz, _sz, _i32, _i32, _vpp]),
     "b2s_ring_destroy": (None, [_vp]),
     "b2s_ring_acquire_empty": (_i32, [_vp, _vpp]),
@@ -95,6 +100,20 @@ SIGNATURES = {
     "b2s_slot_wait": (_i32, [_vp]),
     "b2s_ring_free_slots": (_sz, [_vp]),
     "b2s_ring_full_slots": (_sz, [_vp]),
+    "b2s_ring_base": (_vp, [_vp]),
+    "b2s_ring_bytes": (_sz, [_vp]),
+    "b2s_ring_slot_offset": (_sz, [_vp, _i32]),
+    "b2s_ring_flags_offset": (_sz, [_vp]),
+    "b2s_slot_index": (_i32, [_vp]),
+    "b2s_ipc_export": (_i32, [_vp, _vp, _vp]),
+    "b2s_ipc_open": (_i32, [_vp, _vp, _vpp]),
+    "b2s_ipc_close": (_i32, [_vp, _vp]),
+    "b2s_peer_enable": (_i32, [_vp, _i32]),
+    "b2s_flag_set": (_i32, [_vp, _vp, C.c_uint32]),
+    "b2s_flag_wait": (_i32, [_vp, _vp, C.c_uint32]),
+    "b2s_flag_read": (_i32, [_vp, _vp, C.POINTER(C.c_uint32)]),
+    "b2s_memcpy_d2d": (_i32, [_vp, _vp, _vp, _sz]),
+    "b2s_memset": (_i32, [_vp, _vp, _i32, _sz]),
     "b2s_firdes_kaiser_lowpass": (_sz, [C.c_double, C.c_double, C.c_double, _f32p, _sz]),
     "b2s_firdes_kaiser_multirate": (_sz, [_sz, _sz, _sz, C.c_double, _f32p, _sz]),
 }

@@ -441,6 +441,51 @@ class MovingAvg(Block):
             self._h = None
 
 
+class SpectrumPipe(Block):
+    """The spectrum flowgraph's compute chain as ONE block (SURVEY 8f-3): ``Fft::with_options(n, Forward,
+    fft_shift, None)`` -> ``Apply(|x|^2)`` -> ``MovingAvg<n>::new(decay_factor, history_size)`` of
+    examples/spectrum/src/bin/cpu.rs:21-28, optionally followed by ``log10_scale * log10(.)`` (what the
+    reference's CubeCL kernel fuses, perf/burn/src/bin/fft-cubecl-kernel.rs:115-146).  Complex<f32> in, f32 out;
+    only 8 B/sample in and ``n`` floats per ``history_size`` frames out touch HBM.  Values agree with the three
+    separate blocks to rounding (blocked-scan evaluation of the average), counts are MovingAvg's."""
+    in_dtype = np.complex64
+    out_dtype = np.float32
+
+    def __init__(self, n: int, decay_factor: float, history_size: int, fft_shift: bool = True,
+                 log10_scale: float = 0.0, ctx: Optional[Context] = None):
+        assert 0.0 <= decay_factor <= 1.0, "decay_factor must be in [0, 1]"       # moving_avg.rs:58-61
+        self.ctx = ctx or default_context()
+        self.n = int(n)
+        self._h = C.c_void_p()
+        check(lib.b2s_spectrum_plan(self.ctx.handle, self.n, int(bool(fft_shift)), float(decay_factor), int(history_size),
+                                    float(log10_scale), C.byref(self._h)), self.ctx.handle)
+        self._ports()
+
+    def process(self, x: torch.Tensor, out: torch.Tensor):
+        """(consumed items, produced floats) for device slices -- the call ``work`` makes."""
+        c, p = C.c_size_t(0), C.c_size_t(0)
+        check(lib.b2s_spectrum_exec(self._h, C.c_void_p(x.data_ptr()), x.numel(), C.c_void_p(out.data_ptr()), out.numel(),
+                                    C.byref(c), C.byref(p)), self.ctx.handle)
+        return c.value, p.value
+
+    def work(self, io: WorkIo):
+        i, o = self.input.slice(), self.output.slice()
+        input_len = i.numel()
+        c, p = self.process(i, o)
+        if self.input.finished() and c // self.n == input_len // self.n:          # moving_avg.rs:106-108
+            io.finished = True
+        self.input.consume(c)
+        self.output.produce(p)
+
+    def reset(self):
+        check(lib.b2s_spectrum_reset(self._h), self.ctx.handle)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.b2s_spectrum_destroy(self._h)
+            self._h = None
+
+
 class PfbChannelizer(Block):
     """blocks::PfbChannelizer (src/blocks/pfb/channelizer.rs:72-223): one input, N output streams.
     The N output ports share one channel-major device buffer ``outputs`` of shape [N, capacity];

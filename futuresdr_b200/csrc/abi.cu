@@ -1,6 +1,7 @@
 // abi.cu -- context, memory and FIR entry points of the C ABI (include/b200sdr.h).
 #include <cmath>
 #include <cstdlib>
+#include <memory>
 
 #include "fir.cuh"
 
@@ -30,19 +31,17 @@ static int32_t ctx_create(int device, void *stream, bool own, b2s_ctx **out) {
         return b2s_fail(nullptr, B2S_ECUDA, "no CUDA device: %s", cudaGetErrorString(e));
     if (device < 0 || device >= ndev)
         return b2s_fail(nullptr, B2S_EINVAL, "device %d out of range (%d devices)", device, ndev);
-    b2s_ctx *ctx = new b2s_ctx();
+    std::unique_ptr<b2s_ctx> guard(new b2s_ctx());      // freed on every early return below
+    b2s_ctx *ctx = guard.get();
     ctx->device = device;
-    B2S_CUDA(ctx, cudaSetDevice(device));
+    DeviceGuard dg(device);
     cudaDeviceProp prop;
     B2S_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if (prop.major < 10) {
-        int32_t rc = b2s_fail(nullptr, B2S_EUNSUPPORTED,
-                              "device %d is sm_%d%d; libb200sdr is built for sm_100a only", device,
-                              prop.major, prop.minor);
-        delete ctx;
-        return rc;
+        return b2s_fail(nullptr, B2S_EUNSUPPORTED, "device %d is sm_%d%d; libb200sdr is built for sm_100a only",
+                        device, prop.major, prop.minor);
     }
     if (!own) {
         ctx->stream = (cudaStream_t)stream;
@@ -52,7 +51,9 @@ static int32_t ctx_create(int device, void *stream, bool own, b2s_ctx **out) {
     }
     B2S_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     B2S_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    *out = ctx;
+    B2S_CUDA(ctx, cudaMalloc((void **)&ctx->d_status, 256));
+    B2S_CUDA(ctx, cudaMemset(ctx->d_status, 0, 256));
+    *out = guard.release();
     return B2S_OK;
 }
 
@@ -66,6 +67,7 @@ void b2s_ctx_destroy(b2s_ctx *ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+    if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -81,6 +83,15 @@ int32_t b2s_ctx_sync(b2s_ctx *ctx) {
     if (!ctx) return b2s_fail(nullptr, B2S_EINVAL, "ctx is NULL");
     DeviceGuard g(ctx->device);
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->flag_ops) {                       // cross-GPU handshakes were queued: did one of them time out?
+        unsigned st = 0;
+        B2S_CUDA(ctx, cudaMemcpy(&st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+        ctx->flag_ops = 0;
+        if (st) {
+            cudaMemset(ctx->d_status, 0, sizeof(st));
+            return b2s_fail(ctx, B2S_ETIMEOUT, "a cross-GPU flag wait timed out (status 0x%x): the peer never published its chunk", st);
+        }
+    }
     return B2S_OK;
 }
 
@@ -138,10 +149,19 @@ int32_t b2s_memcpy_d2h(b2s_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
 static constexpr size_t kTensorMinTaps = 24;
 // Long filters (beyond the tensor kernel's 257 taps) go to the overlap-save FFT kernel.
 static constexpr size_t kFftMinTaps = 258;
+// Constant tap vectors (boxcar / moving-average / CIC-like filters): every partial-product error of the split-bf16
+// tensor path has the same sign there, and on DC-heavy input they add coherently up to ~3e-5 of ||taps||_1 max|x|
+// (tests/test_gpu_fir_tensor_structured.py) -- AUTO keeps those on the CUDA cores (exact f32 products).
+static bool taps_constant(const b2s_fir *f) {
+    if (f->kind == B2S_C32_C32) return false;
+    for (size_t i = 1; i < f->ntaps; i++)
+        if (f->taps_host[i] != f->taps_host[0]) return false;
+    return true;
+}
 static void resolve_algo(b2s_fir *f) {
     if (f->algo_req == B2S_ALGO_TENSOR && fir_tc_supported(f)) f->algo = B2S_ALGO_TENSOR;
     else if (f->algo_req == B2S_ALGO_FFT && fir_fft_supported(f)) f->algo = B2S_ALGO_FFT;
-    else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= kTensorMinTaps)
+    else if (f->algo_req == B2S_ALGO_AUTO && fir_tc_supported(f) && f->ntaps >= kTensorMinTaps && !taps_constant(f))
         f->algo = B2S_ALGO_TENSOR;
     else if (f->algo_req == B2S_ALGO_AUTO && fir_fft_supported(f) &&
              (f->ntaps >= kFftMinTaps || (f->kind == B2S_C32_C32 && f->ntaps >= 128)))
@@ -203,7 +223,7 @@ int32_t b2s_fir_set_algo(b2s_fir *f, b2s_algo algo) {
     if (!f) return b2s_fail(nullptr, B2S_EINVAL, "fir is NULL");
     if (algo == B2S_ALGO_TENSOR && !fir_tc_supported(f))
         return b2s_fail(f->ctx, B2S_EUNSUPPORTED,
-                        "tensor algorithm needs real taps, 16..257 of them, and decim == 1 (kind %d, ntaps %zu, decim %zu)",
+                        "tensor algorithm needs real taps, 16..257 of them, and a decimation that divides 128 (kind %d, ntaps %zu, decim %zu)",
                         (int)f->kind, f->ntaps, f->decim);
     if (algo == B2S_ALGO_FFT && !fir_fft_supported(f))
         return b2s_fail(f->ctx, B2S_EUNSUPPORTED,
@@ -262,6 +282,9 @@ int32_t b2s_fir_filter_host(b2s_fir *f, const void *h_in, size_t n_in, void *h_o
     if (n_out == 0) return B2S_OK;
     if (!h_in || !h_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_filter_host: NULL buffer");
     DeviceGuard g(ctx->device);
+    // One host pipeline per context at a time: the workspace, the side streams and the events are shared by every
+    // plan of the context (Filter::filter is re-entrant in the reference; here concurrent callers queue up).
+    std::lock_guard<std::mutex> lk(ctx->host_mu);
 
     const size_t isz = kind_in_bytes(f->kind), D = f->decim, N = f->ntaps;
     constexpr int NSLOT = 4;
@@ -276,28 +299,32 @@ int32_t b2s_fir_filter_host(b2s_fir *f, const void *h_in, size_t n_in, void *h_o
     const size_t in_bytes = round_up(in_items * isz, 256), out_bytes = round_up(CH * isz, 256);
     const size_t need = NSLOT * (in_bytes + out_bytes);
     if (ctx->ws_bytes < need) {
-        if (ctx->ws_dev) { B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ws_dev); }
+        if (ctx->ws_dev) {
+            // nothing queued on any of the three streams may still touch the old workspace
+            B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            B2S_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
+            B2S_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+            cudaFree(ctx->ws_dev);
+        }
         ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
         cudaError_t e = cudaMalloc(&ctx->ws_dev, need);
         if (e != cudaSuccess) { cudaGetLastError(); return b2s_fail(ctx, B2S_ENOMEM, "workspace %zu B", need); }
         ctx->ws_bytes = need;
     }
     char *base = (char *)ctx->ws_dev;
-    cudaEvent_t ev_in[NSLOT], ev_k[NSLOT], ev_out[NSLOT];
-    for (int s = 0; s < NSLOT; s++) {
-        B2S_CUDA(ctx, cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
-        B2S_CUDA(ctx, cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming));
-        B2S_CUDA(ctx, cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming));
+    if (!ctx->hev_ready) {
+        for (int i = 0; i < 3 * NSLOT + 1; i++) B2S_CUDA(ctx, cudaEventCreateWithFlags(&ctx->hev[i], cudaEventDisableTiming));
+        ctx->hev_ready = true;
     }
+    cudaEvent_t *ev_in = ctx->hev, *ev_k = ctx->hev + NSLOT, *ev_out = ctx->hev + 2 * NSLOT, ev0 = ctx->hev[3 * NSLOT];
     int32_t rc = B2S_OK;
     const size_t nchunks = ceil_div(n_out, CH);
     // the copies must not start before work already queued on the context stream that may
     // still use the workspace
-    cudaEvent_t ev0;
-    B2S_CUDA(ctx, cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
     B2S_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     B2S_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev0, 0));
     B2S_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev0, 0));
+    nvtx_push("b2s_fir_filter_host");
     for (size_t c = 0; c < nchunks && rc == B2S_OK; c++) {
         const int s = (int)(c % NSLOT);
         char *din = base + (size_t)s * (in_bytes + out_bytes), *dout = din + in_bytes;
@@ -321,12 +348,48 @@ int32_t b2s_fir_filter_host(b2s_fir *f, const void *h_in, size_t n_in, void *h_o
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_d2h);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaError_t e3 = cudaStreamSynchronize(ctx->s_h2d);
-    for (int s = 0; s < NSLOT; s++) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_k[s]); cudaEventDestroy(ev_out[s]); }
-    cudaEventDestroy(ev0);
+    nvtx_pop();
     if (rc != B2S_OK) return rc;
     B2S_CUDA(ctx, e1); B2S_CUDA(ctx, e2); B2S_CUDA(ctx, e3);
     B2S_CUDA(ctx, cudaGetLastError());
     return B2S_OK;
+}
+
+// ≙ Filter::filter on the logical slice  hist[0..n_hist) ++ in[0..n_in)  (include/b200sdr.h).
+int32_t b2s_fir_exec_hist(b2s_fir *f, const void *d_hist, size_t n_hist, const void *d_in, size_t n_in,
+                          void *d_out, size_t n_out_cap, const uint32_t *wait_flag, uint32_t wait_value,
+                          uint32_t *done_flag, uint32_t done_value, size_t *consumed, size_t *produced,
+                          int32_t *status) {
+    if (!f || !consumed || !produced || !status)
+        return b2s_fail(f ? f->ctx : nullptr, B2S_EINVAL, "b2s_fir_exec_hist: NULL argument");
+    b2s_ctx *ctx = f->ctx;
+    if (n_hist && !d_hist) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_exec_hist: NULL history");
+    fir_counts(f, n_hist + n_in, n_out_cap, consumed, produced, status);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    auto handshake_only = [&]() -> int32_t {      // nothing to compute: still honour the flag protocol
+        if (wait_flag) { int32_t rc = peer_flag_wait_launch(ctx, wait_flag, wait_value, st); if (rc) return rc; }
+        if (done_flag) return peer_flag_set_launch(ctx, done_flag, done_value, st);
+        return B2S_OK;
+    };
+    if (*produced == 0) return handshake_only();
+    if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_exec_hist: NULL buffer");
+    FirHist h;
+    h.d_hist = d_hist; h.n_hist = n_hist;
+    h.wait_flag = wait_flag; h.wait_value = wait_value; h.done_flag = done_flag; h.done_value = done_value;
+    if (f->algo == B2S_ALGO_TENSOR && n_hist) {
+        const int32_t rc = fir_tc_launch_hist(f, &h, d_in, n_in, d_out, *produced, st);   // fused: the loader fetches hist
+        if (rc != B2S_EAGAIN) return rc;
+    }
+    // every other path wants one contiguous slice: install the history in the n_hist items in front of d_in (the
+    // caller guarantees they are writable scratch of the same allocation -- a ring slot's halo region)
+    if (wait_flag) { int32_t rc = peer_flag_wait_launch(ctx, wait_flag, wait_value, st); if (rc) return rc; }
+    const size_t isz = kind_in_bytes(f->kind);
+    char *dst = (char *)const_cast<void *>(d_in) - n_hist * isz;
+    if (n_hist && dst != (const char *)d_hist)
+        B2S_CUDA(ctx, cudaMemcpyAsync(dst, d_hist, n_hist * isz, cudaMemcpyDefault, st));
+    if (done_flag) { int32_t rc = peer_flag_set_launch(ctx, done_flag, done_value, st); if (rc) return rc; }
+    return fir_launch(f, dst, n_hist + n_in, d_out, *produced, st);
 }
 
 }  // extern "C"

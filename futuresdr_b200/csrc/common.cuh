@@ -28,6 +28,15 @@ struct b2s_ctx {
     // workspace for *_host calls (grown on demand, freed with the context)
     void *ws_dev = nullptr;
     size_t ws_bytes = 0;
+    cudaEvent_t hev[16] = {};      // events of the host-slice pipeline, created once
+    bool hev_ready = false;
+    std::mutex host_mu;            // serialises the *_host pipelines that share the workspace and side streams
+    // device status word (bit0: a cross-GPU flag wait timed out); checked by b2s_ctx_sync when flag_ops > 0
+    unsigned *d_status = nullptr;
+    uint64_t flag_ops = 0;
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE, and a process may hold contexts on several:
+    // opt-in state lives here, one bit per kernel family (fir_direct.cu, fft.cu)
+    uint32_t smem_optin_done = 0;
 };
 
 extern thread_local std::string g_b2s_last_error;
@@ -59,6 +68,13 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// peer.cu: NVTX ranges (visible to nsys / ncu --nvtx) and the cross-GPU flag kernels
+void nvtx_push(const char *name);
+void nvtx_pop();
+struct NvtxRange { explicit NvtxRange(const char *n) { nvtx_push(n); } ~NvtxRange() { nvtx_pop(); } };
+int32_t peer_flag_set_launch(b2s_ctx *ctx, unsigned *flag, unsigned value, cudaStream_t st);
+int32_t peer_flag_wait_launch(b2s_ctx *ctx, const unsigned *flag, unsigned value, cudaStream_t st);
 
 static inline size_t sat_sub(size_t a, size_t b) { return a > b ? a - b : 0; }
 static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -35,8 +35,20 @@ bool    resamp_slide_supported(size_t L, size_t M, size_t T, size_t item_bytes);
 void    resamp_slide_table(const float *taps, size_t L, size_t M, size_t T, std::vector<float> &g);
 int32_t resamp_slide_launch(b2s_ctx *ctx, b2s_kind kind, const float *d_gtab, size_t L, size_t M, size_t T,
                             const void *d_in, size_t n_in, void *d_out, size_t n_out, cudaStream_t stream);
+// detached history of b2s_fir_exec_hist: n_hist items that logically precede the slice, plus the optional
+// cross-GPU handshake (system-scope flags in device memory, see peer.cu)
+struct FirHist {
+    const void *d_hist = nullptr;
+    size_t n_hist = 0;
+    const unsigned *wait_flag = nullptr;
+    unsigned wait_value = 0;
+    unsigned *done_flag = nullptr;
+    unsigned done_value = 0;
+};
 // fir_tc.cu
 bool    fir_tc_supported(const b2s_fir *f);
+int32_t fir_tc_launch_hist(b2s_fir *f, const FirHist *h, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                           cudaStream_t stream);
 int32_t fir_tc_prepare(b2s_fir *f);
 int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                       cudaStream_t stream);

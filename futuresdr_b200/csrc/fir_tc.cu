@@ -241,6 +241,20 @@ struct TcParams {
     int flags;            // bit0: swap bf16 halves of the TMEM A words (bring-up switch)
     int out_bulk;         // out is 16-byte aligned: interior tiles leave through bulk (TMA) stores
     int decim;            // D | 128: only the output phases p == D-1 (mod D) are stored (decimating FIR)
+    // ---- misaligned / detached history (b2s_fir_exec_hist) -------------------------------------------------
+    // The kernel's item coordinate i is:  [0, lead) dummy items that only exist to keep every bulk copy 16-byte
+    // aligned (zeroed by the converters; the Toeplitz operand is shifted by `lead` columns so they meet zero
+    // taps), [lead, hist_items) the detached history (`hist`, possibly PEER memory of the left-neighbour GPU,
+    // fetched by the TMA loader over NVLink), [hist_items, n_in) the caller's slice.  `in` is the VIRTUAL base:
+    // in + i addresses item i for i >= hist_items (hist_items == 0: everything is contiguous from `in`).
+    const float *hist;    // 16-byte aligned address of item 0 when hist_items > 0
+    int hist_items;       // lead + n_hist (a whole number of 16-byte units), 0 = contiguous input
+    int lead;
+    const unsigned *wait_flag;   // spin until *wait_flag >= wait_value (system scope) before reading hist
+    unsigned wait_value;
+    unsigned *done_flag;         // *done_flag = done_value (release, system scope) once hist sits in shared memory
+    unsigned done_value;
+    unsigned *status;            // device status word of the context: bit0 = a flag wait timed out
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int k0 = 2 * (c0 + i) - p, k1 = k0 + 1;
+                const int k0 = 2 * (c0 + i) - p - prm.lead, k1 = k0 + 1;   // `lead` zero taps in front (dummy items)
                 const float g0 = (k0 >= 0 && k0 < prm.ntaps) ? gs[k0] : 0.0f;
                 const float g1 = (k1 >= 0 && k1 < prm.ntaps) ? gs[k1] : 0.0f;
                 if (prm.flags & 1) split2(g1, g0, hi[i], lo[i]);
@@ -369,7 +383,32 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                     TCT_LAP(1)
                     mbar_wait(rempty_bar(rs), rphase ^ 1);
                     TCT_LAP(0)
-                    if (bytes > 0) {
+                    if (tile == 0 && s == 0 && prm.hist_items > 0) {
+                        // detached history: items [0, hist_items) come from `hist` (the left neighbour's tail over
+                        // NVLink when it is peer memory), the rest of the slot from the caller's slice.
+                        if (prm.wait_flag) {
+                            unsigned long long t0, t1;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                            for (;;) {
+                                unsigned v;
+                                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(prm.wait_flag) : "memory");
+                                if ((int)(v - prm.wait_value) >= 0) break;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                                if (t1 - t0 > 4000000000ull) { atomicOr(prm.status, 1u); break; }   // 4 s: give up, flag it
+                                __nanosleep(64);
+                            }
+                            asm volatile("fence.proxy.async;" ::: "memory");   // acquire (generic) -> bulk copy (async proxy)
+                        }
+                        const uint32_t hb = (uint32_t)prm.hist_items * ITEM_BYTES;
+                        const uint32_t rest = bytes > (long long)hb ? (uint32_t)bytes - hb : 0u;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rfull_bar(rs)), "r"(hb + rest) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(raw_base + rs * kRawSlotBytes), "l"(prm.hist), "r"(hb), "r"(rfull_bar(rs)) : "memory");
+                        if (rest)
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(raw_base + rs * kRawSlotBytes + hb), "l"(prm.in + (COMPLEX ? 2 : 1) * (long long)prm.hist_items),
+                                           "r"(rest), "r"(rfull_bar(rs)) : "memory");
+                    } else if (bytes > 0) {
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rfull_bar(rs)), "r"((uint32_t)bytes) : "memory");
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                      ::"r"(raw_base + rs * kRawSlotBytes), "l"(prm.in + (COMPLEX ? 2 : 1) * it0),
@@ -422,6 +461,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                 v[1] = raw[tid + 256];
                 const int rs_cur = rs;
                 if (++rs == kRawSlots) { rs = 0; rphase ^= 1; }
+                if constexpr (!INTERIOR) {
+                    // the detached history has landed in shared memory: tell its owner it may be overwritten
+                    if (s == 0 && item0 == 0 && tid == 0 && prm.done_flag)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(prm.done_flag), "r"(prm.done_value) : "memory");
+                }
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     constexpr int ROWS = COMPLEX ? 4 : 8;
@@ -440,9 +484,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
                         const long long gf = it * (COMPLEX ? 2 : 1);
                         const long long total_f = prm.n_in * (COMPLEX ? 2 : 1), copied_f = total_f & ~3ll;
                         float *e = reinterpret_cast<float *>(&v[i]);
+                        const long long lead_f = (long long)prm.lead * (COMPLEX ? 2 : 1);
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
-                            if (gf + c >= total_f) e[c] = 0.0f;
+                            if (gf + c >= total_f || gf + c < lead_f) e[c] = 0.0f;
                             else if (gf + c >= copied_f) e[c] = prm.in[gf + c];
                         }
                     }
@@ -489,7 +534,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         uint32_t phase = 0, rphase = 0;
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             const long long item0 = (long long)tile * TILE_ITEMS;
-            const bool interior = item0 + (long long)in_blocks * 128 <= prm.n_in;
+            const bool interior = item0 + (long long)in_blocks * 128 <= prm.n_in &&
+                                  !(tile == 0 && (prm.lead | prm.hist_items) != 0);   // tile 0 zeroes the dummy items
             TCT_LAP(1)
             mbar_wait(empty_bar(stage), phase ^ 1);
             TCT_LAP(0)
@@ -526,7 +572,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             // Toeplitz columns kappa >= ntaps + 127 hold no tap: skip those K-steps
-                            if (d * 128 + kc * 64 + ks * 16 >= prm.ntaps + 127) continue;
+                            if (d * 128 + kc * 64 + ks * 16 >= prm.ntaps + prm.lead + 127) continue;
                             const uint32_t kcol = (uint32_t)(d * 64 + kc * 32 + ks * 8);       // A column (2 bf16 / column)
                             const uint32_t boff = (uint32_t)(kc * chunk_bytes + d * 1024 + ks * 32);
                             const uint64_t bh = make_b_desc(sbase + boff);
@@ -680,29 +726,57 @@ int32_t fir_tc_prepare(b2s_fir *f) {
 
 void fir_tc_release(b2s_fir *f) { f->tc_ready = false; }
 
-int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
-                      cudaStream_t stream) {
+// The tensor kernel moves its input with 16-byte bulk copies.  A slice that starts on an item boundary but not on a
+// 16-byte one (a ring slot's [halo | chunk] with 255 items of history, say) is handled by starting `lead` items
+// early and shifting the Toeplitz operand by `lead` zero taps; a DETACHED history (hist, possibly peer memory) is
+// fetched by the loader in front of tile 0.  Returns B2S_EAGAIN when this call cannot run on the tensor kernel
+// (the caller then copies the history in place and/or uses the CUDA-core kernel).
+int32_t fir_tc_launch_hist(b2s_fir *f, const FirHist *h, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                           cudaStream_t stream) {
     b2s_ctx *ctx = f->ctx;
     if (n_out == 0) return B2S_OK;
     if (!f->tc_ready) return b2s_fail(ctx, B2S_ESTATE, "tensor FIR not prepared");
-    // vector loads / float2 stores need natural alignment; otherwise use the direct kernel
     const bool cplx = f->kind == B2S_C32_F32;
-    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & (cplx ? 7 : 3)))
-        return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);
+    const size_t item = cplx ? 8 : 4, q = 16 / item;
+    const uintptr_t a_in = reinterpret_cast<uintptr_t>(d_in), a_out = reinterpret_cast<uintptr_t>(d_out);
+    if ((a_in % item) || (a_out % item)) return B2S_EAGAIN;
+    const size_t n_hist = h ? h->n_hist : 0;
+    size_t lead;
+    if (n_hist) {
+        const uintptr_t a_h = reinterpret_cast<uintptr_t>(h->d_hist);
+        if ((a_h % item) || (a_in & 15)) return B2S_EAGAIN;
+        lead = (a_h / item) % q;
+        if ((lead + n_hist) % q) return B2S_EAGAIN;
+        if (lead + n_hist > 1024 || n_in * item < 16) return B2S_EAGAIN;     // must fit the first raw slot
+    } else {
+        lead = (a_in / item) % q;
+    }
+    const int DK = (int)ceil_div(f->ntaps + lead + 127, 128);
+    if (DK > kMaxDK) return B2S_EAGAIN;
     TcParams prm;
-    prm.in = (const float *)d_in;
+    prm.lead = (int)lead;
+    prm.hist_items = n_hist ? (int)(lead + n_hist) : 0;
+    prm.hist = n_hist ? (const float *)h->d_hist - lead * (item / 4) : nullptr;
+    // virtual base: item i of the kernel's coordinate lives at in + i for i >= hist_items
+    prm.in = (const float *)d_in - (lead + n_hist) * (item / 4);
+    prm.wait_flag = (h && n_hist) ? h->wait_flag : nullptr;
+    prm.wait_value = h ? h->wait_value : 0;
+    prm.done_flag = (h && n_hist) ? h->done_flag : nullptr;
+    prm.done_value = h ? h->done_value : 0;
+    prm.status = ctx->d_status;
     prm.out = (float *)d_out;
     prm.g = f->d_ptaps + (size_t)f->decim * f->Upad;      // plain reversed taps (fir_direct_prepare)
-    prm.n_in = (long long)n_in;
+    prm.n_in = (long long)(lead + n_hist + n_in);
     prm.n_out = (long long)n_out;                        // decimated count
     prm.decim = (int)f->decim;
     prm.ntaps = (int)f->ntaps;
-    prm.DK = f->tc_kblocks;
+    prm.DK = DK;
     const long long tile_items = cplx ? 64 * 128 : 128 * 128;
     prm.num_tiles = (int)ceil_div(n_out * f->decim, (size_t)tile_items);   // tiles over the full-rate index space
     prm.flags = f->tc_flags;
-    prm.out_bulk = (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !(f->tc_flags & 16);   // flags bit4: force per-lane stores
+    prm.out_bulk = (a_out & 15) == 0 && !(f->tc_flags & 16);   // flags bit4: force per-lane stores
     const int grid = std::min(prm.num_tiles, ctx->sm_count);
+    if (prm.wait_flag || prm.done_flag) ctx->flag_ops++;
     if (cplx) fir_tc_kernel<true><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
     else fir_tc_kernel<false><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
     B2S_CHECK_LAUNCH(ctx);
@@ -727,4 +801,11 @@ int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, si
     }
 #endif
     return B2S_OK;
+}
+
+int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
+                      cudaStream_t stream) {
+    const int32_t rc = fir_tc_launch_hist(f, nullptr, d_in, n_in, d_out, n_out, stream);
+    if (rc == B2S_EAGAIN) return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);   // item-misaligned slices
+    return rc;
 }

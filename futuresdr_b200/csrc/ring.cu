@@ -36,6 +36,7 @@ struct b2s_ring {
     mutable std::mutex mu;
     char *d_mem = nullptr;
     char *h_mem = nullptr;
+    size_t slot_bytes = 0, halo_bytes = 0, total_bytes = 0, flags_off = 0;
 };
 
 extern "C" {
@@ -52,8 +53,13 @@ int32_t b2s_ring_create(b2s_ctx *ctx, size_t item_bytes, size_t chunk_items, siz
     const size_t halo_bytes = round_up(halo_items * item_bytes, 256);
     const size_t data_bytes = round_up(chunk_items * item_bytes, 256);
     const size_t slot_bytes = halo_bytes + data_bytes;
-    cudaError_t e = cudaMalloc((void **)&r->d_mem, slot_bytes * n_slots);
-    if (e != cudaSuccess) { cudaGetLastError(); delete r; return b2s_fail(ctx, B2S_ENOMEM, "ring: %zu bytes of device memory", slot_bytes * n_slots); }
+    // ONE allocation (so one CUDA-IPC handle exports the whole ring to a peer process): slots, then 256 bytes of
+    // system-scope flags {ready, consumed} for the cross-GPU halo handshake (peer.cu)
+    r->slot_bytes = slot_bytes; r->halo_bytes = halo_bytes; r->flags_off = slot_bytes * n_slots;
+    r->total_bytes = r->flags_off + 256;
+    cudaError_t e = cudaMalloc((void **)&r->d_mem, r->total_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); delete r; return b2s_fail(ctx, B2S_ENOMEM, "ring: %zu bytes of device memory", r->total_bytes); }
+    cudaMemsetAsync(r->d_mem + r->flags_off, 0, 256, ctx->stream);
     if (with_host_staging) {
         e = cudaHostAlloc((void **)&r->h_mem, data_bytes * n_slots, cudaHostAllocDefault);
         if (e != cudaSuccess) { cudaGetLastError(); cudaFree(r->d_mem); delete r; return b2s_fail(ctx, B2S_ENOMEM, "ring: pinned staging"); }
@@ -176,6 +182,15 @@ int32_t b2s_slot_wait(b2s_slot *s) {
     B2S_CUDA(s->ring->ctx, cudaEventSynchronize(s->ev));
     return B2S_OK;
 }
+
+void *b2s_ring_base(const b2s_ring *r) { return r ? r->d_mem : nullptr; }
+size_t b2s_ring_bytes(const b2s_ring *r) { return r ? r->total_bytes : 0; }
+size_t b2s_ring_slot_offset(const b2s_ring *r, int32_t slot_index) {
+    if (!r || slot_index < 0 || (size_t)slot_index >= r->slots.size()) return 0;
+    return (size_t)slot_index * r->slot_bytes + r->halo_bytes;
+}
+size_t b2s_ring_flags_offset(const b2s_ring *r) { return r ? r->flags_off : 0; }
+int32_t b2s_slot_index(const b2s_slot *s) { return s ? s->index : -1; }
 
 size_t b2s_ring_free_slots(const b2s_ring *r) {
     if (!r) return 0;

@@ -17,6 +17,16 @@ the first ``H/D`` outputs waits for the neighbour's tail.
 
 The per-rank compute is the same C-ABI FIR plan as the single-GPU path; ``compute`` can be
 replaced (tests run this file's logic on CPU over gloo with the oracle as the kernel).
+
+``exchange="peer"`` (the default on GPUs) removes even that from the step: every rank keeps its chunks in a
+C-ABI device ring (``b2s_ring_*``) exported to its right neighbour through CUDA IPC, and the FIR kernel's
+TMA loader fetches the left neighbour's last ``H`` samples straight from the neighbour's HBM over NVLink in
+front of its first tile (``b2s_fir_exec_hist``) -- ONE launch per step, no copy, no collective, no host
+synchronisation.  Ordering is two u32 counters per ring in device memory: ``ready`` (chunks published by the
+owner, release store) which the neighbour's kernel spins on before it reads the tail, and ``consumed``
+(written back by that kernel) which the owner's stream waits on before it refills the slot.  NCCL is only
+used to bootstrap (exchange of the 64-byte IPC handles).  ``exchange="nccl"`` keeps the all-gather variant
+(the north star's wording; also what the gloo tests exercise on CPU).
 """
 from __future__ import annotations
 
@@ -32,7 +42,8 @@ from . import _lib
 class ShardedFir:
     def __init__(self, taps, chunk_items: int, sample_dtype=np.complex64, decim: int = 1,
                  device: Optional[torch.device] = None, group=None,
-                 compute: Optional[Callable] = None, algo: int = 0, overlap: bool = True):
+                 compute: Optional[Callable] = None, algo: int = 0, overlap: bool = True,
+                 exchange: str = "auto", n_slots: int = 2):
         self.taps = np.ascontiguousarray(taps)
         self.ntaps = int(self.taps.size)
         self.S = int(chunk_items)
@@ -57,31 +68,163 @@ class ShardedFir:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.tdtype = torch.complex64 if np.dtype(sample_dtype) == np.complex64 else torch.float32
+        self.sample_dtype = np.dtype(sample_dtype)
+        if exchange == "auto":
+            exchange = "peer" if (compute is None and self.device.type == "cuda") else "nccl"
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self.exchange = exchange
+        self.have_history = False          # becomes True after the first step of the stream
+        self.step_index = 0
+        self.overlap = bool(overlap)
+        self.on_kernel = None              # optional callable("begin" | "end") around the FIR launch (bench timing)
+        if exchange == "peer":
+            self._init_peer(algo, int(n_slots))
+            return
         # [halo | chunk] contiguous so the kernel sees history + new samples as one slice
         self.xbuf = torch.zeros(self.halo + self.S, dtype=self.tdtype, device=self.device)
         self.tails = torch.zeros(self.world, max(self.halo, 1), dtype=self.tdtype, device=self.device)
         self.my_tail = torch.zeros(max(self.halo, 1), dtype=self.tdtype, device=self.device)
         self.prev_last_tail = torch.zeros(max(self.halo, 1), dtype=self.tdtype, device=self.device)
-        self.have_history = False          # becomes True after the first step of the stream
-        self.step_index = 0
-        self.overlap = bool(overlap)
         if compute is None:
             from .filters import DecimatingFirFilter
-            self._filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, algo=algo)
+            ctx = self._make_ctx()
+            self._filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, ctx=ctx, algo=algo)
             compute = self._filter.filter
             # the split/D outputs behind the exchange are a few hundred items: the CUDA-core kernel has no
             # TMEM / tap-table prologue, so that second launch costs ~half of a tensor-kernel launch
-            self._head_filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, algo=_lib.ALGO_DIRECT)
+            self._head_filter = DecimatingFirFilter(self.decim, self.taps, sample_dtype, ctx=ctx, algo=_lib.ALGO_DIRECT)
             head_compute = self._head_filter.filter
         else:
             head_compute = compute
         self.compute = compute
         self.head_compute = head_compute
 
+    def _make_ctx(self):
+        """The context of THIS object's device and of torch's current stream there (not whatever device happens
+        to be current): buffers, kernels and collectives must share one device and one stream order."""
+        from .context import Context
+        return Context(self.device.index if self.device.index is not None else torch.cuda.current_device(),
+                       stream=torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------------
+    # exchange == "peer": device ring + CUDA-IPC peer mapping + in-kernel history fetch
+    # ------------------------------------------------------------------------------------------------
+    def _init_peer(self, algo: int, n_slots: int):
+        import ctypes as C
+        from ._lib import lib, check
+        from .filters import DecimatingFirFilter
+        if n_slots < 2:
+            raise ValueError("the peer exchange needs at least two ring slots")
+        self.ctx = self._make_ctx()
+        self._filter = DecimatingFirFilter(self.decim, self.taps, self.sample_dtype, ctx=self.ctx, algo=algo)
+        self.n_slots = n_slots
+        isz = self.sample_dtype.itemsize
+        if (self.S * isz) % 16:
+            raise ValueError("chunk_items must be a whole number of 16-byte units for the peer exchange")
+        self._ring = C.c_void_p()
+        check(lib.b2s_ring_create(self.ctx.handle, isz, self.S, max(self.halo, 1), n_slots, 0, C.byref(self._ring)),
+              self.ctx.handle)
+        self._base = lib.b2s_ring_base(self._ring)
+        self._slot_off = [lib.b2s_ring_slot_offset(self._ring, i) for i in range(n_slots)]
+        self._flags_off = lib.b2s_ring_flags_offset(self._ring)
+        self._ready = self._base + self._flags_off            # chunks this rank has published
+        self._consumed = self._base + self._flags_off + 4     # chunks whose tail the right neighbour has read
+        self._left_base = self._base                          # world == 1: the "neighbour" is this ring
+        self._left_mapped = None
+        if self.world > 1:
+            h = (C.c_uint8 * 64)()
+            check(lib.b2s_ipc_export(self.ctx.handle, C.c_void_p(self._base), h), self.ctx.handle)
+            mine = {"handle": bytes(h), "slot_off": self._slot_off, "flags_off": self._flags_off, "pid": __import__("os").getpid(),
+                    "device": self.ctx.device}
+            allh = [None] * self.world
+            dist.all_gather_object(allh, mine, group=self.group)
+            left = allh[(self.rank - 1) % self.world]
+            if left["slot_off"] != self._slot_off or left["flags_off"] != self._flags_off:
+                raise RuntimeError("ring geometry differs between ranks")
+            if left["pid"] == mine["pid"]:
+                raise RuntimeError("peer exchange needs one process per rank")
+            p = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(left["handle"])
+            check(lib.b2s_ipc_open(self.ctx.handle, hb, C.byref(p)), self.ctx.handle)
+            self._left_base = self._left_mapped = p.value
+        self._cur = None          # slot index being filled for the coming step
+        self._slots = [None] * n_slots
+
+    def close(self):
+        if getattr(self, "exchange", None) == "peer" and getattr(self, "_ring", None):
+            from ._lib import lib
+            self.ctx.sync()
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)            # nobody may still be reading this ring
+            if self._left_mapped:
+                lib.b2s_ipc_close(self.ctx.handle, self._left_mapped)
+                self._left_mapped = None
+            lib.b2s_ring_destroy(self._ring)
+            self._ring = None
+
+    def _slot_tensor(self, index: int) -> torch.Tensor:
+        from .edges import _DevView
+        return torch.as_tensor(_DevView(self._base + self._slot_off[index], self.S, self.sample_dtype), device=self.device)
+
+    def slot_tensors(self):
+        """All ring slots as tensors (benchmarks pre-fill them once so that the timed steps find their
+        input resident in HBM)."""
+        return [self._slot_tensor(i) for i in range(self.n_slots)]
+
+    def begin_chunk(self) -> torch.Tensor:
+        """Writable view of the slot of the coming step.  Before the slot is handed out the stream waits until
+        the right neighbour has read the tail of the chunk that last lived in it (``consumed`` counter)."""
+        if self.exchange != "peer":
+            return self.xbuf[self.halo:]
+        if self._cur is None:
+            from ._lib import lib, check
+            t = self.step_index
+            self._cur = t % self.n_slots
+            if self.world > 1 and t >= self.n_slots and self.halo:
+                check(lib.b2s_flag_wait(self.ctx.handle, self._consumed, t - self.n_slots + 1), self.ctx.handle)
+        return self._slot_tensor(self._cur)
+
     @property
     def chunk(self) -> torch.Tensor:
         """The rank's writable chunk (fill this with the step's samples)."""
-        return self.xbuf[self.halo:]
+        return self.begin_chunk()
+
+    def _step_peer(self, out: torch.Tensor):
+        import ctypes as C
+        from ._lib import lib, check
+        self.begin_chunk()
+        t, W, r, H, S = self.step_index, self.world, self.rank, self.halo, self.S
+        isz = self.sample_dtype.itemsize
+        cur = self._cur
+        d_in = self._base + self._slot_off[cur]
+        if W > 1 and H:
+            check(lib.b2s_flag_set(self.ctx.handle, self._ready, t + 1), self.ctx.handle)     # publish chunk t
+        first_of_stream = r == 0 and t == 0
+        c, p, st = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
+        if self.on_kernel:
+            self.on_kernel("begin")
+        if first_of_stream or H == 0:
+            check(lib.b2s_fir_exec(self._filter._h, C.c_void_p(d_in), S, C.c_void_p(out.data_ptr()), out.numel(),
+                                   C.byref(c), C.byref(p), C.byref(st)), self.ctx.handle)
+        else:
+            if r == 0:      # history = the tail of rank W-1's chunk of the PREVIOUS step
+                src_slot, need = (t - 1) % self.n_slots, t
+            else:           # history = the tail of rank r-1's chunk of THIS step
+                src_slot, need = cur, t + 1
+            d_hist = self._left_base + self._slot_off[src_slot] + (S - H) * isz
+            wf = C.c_void_p(self._left_base + self._flags_off) if W > 1 else None
+            df = C.c_void_p(self._left_base + self._flags_off + 4) if W > 1 else None
+            check(lib.b2s_fir_exec_hist(self._filter._h, C.c_void_p(d_hist), H, C.c_void_p(d_in), S,
+                                        C.c_void_p(out.data_ptr()), out.numel(), wf, need, df, need,
+                                        C.byref(c), C.byref(p), C.byref(st)), self.ctx.handle)
+        if self.on_kernel:
+            self.on_kernel("end")
+        self._cur = None
+        self.have_history = True
+        self.step_index += 1
+        from .filters import ComputationStatus
+        return c.value, p.value, ComputationStatus(st.value)
 
     def _exchange(self, async_op: bool):
         """All-gather of the overlap region (every rank's last H samples). Returns a work handle or None."""
@@ -101,6 +244,8 @@ class ShardedFir:
 
         Returns (consumed, produced, status).  ``out`` must hold ``S // decim`` items.
         """
+        if self.exchange == "peer":
+            return self._step_peer(out)
         H, D, N = self.halo, self.decim, self.ntaps
         first_of_stream = self.rank == 0 and not self.have_history
         if self.world == 1:

@@ -40,6 +40,7 @@ extern "C" {
 #define B2S_EAGAIN       (-4) /* ring: no buffer available right now (not an error)         */
 #define B2S_EUNSUPPORTED (-5) /* combination the reference supports but this build does not */
 #define B2S_ESTATE       (-6) /* slot/ring used out of order                                */
+#define B2S_ETIMEOUT     (-7) /* a cross-GPU flag wait gave up (the peer never published)   */
 
 /* futuredsp::ComputationStatus  (crates/futuredsp/src/lib.rs:33-45) */
 #define B2S_INSUFFICIENT_INPUT  0
@@ -112,6 +113,19 @@ int32_t b2s_fir_get_algo(const b2s_fir *f);         /* the algorithm AUTO resolv
  * Elements of d_out beyond *produced are left unspecified, as in the reference. */
 int32_t b2s_fir_exec(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
                      size_t *consumed, size_t *produced, int32_t *status);
+/* Same contract on the LOGICAL slice  d_hist[0..n_hist) ++ d_in[0..n_in):  the history a FIR block keeps in front
+ * of new samples (blocks/fir.rs:49 min_items, slab.rs:370-398) handed over as a separate pointer, so that it can live
+ * in another ring slot -- or in ANOTHER GPU's memory (the last ntaps-1 samples of the left neighbour's
+ * shard; `d_hist` is then a peer address from b2s_ipc_open / b2s_peer_enable).  On the tensor path the kernel's TMA
+ * loader fetches the history itself (over NVLink for peer memory): one launch, no copy, no host synchronisation.
+ * Other paths copy it into the n_hist items in FRONT of d_in, which must therefore be writable scratch of the same
+ * allocation (a ring slot's halo region; b2s_ring_create(..., halo_items >= n_hist, ...)).
+ * Optional handshake (NULL = none): before reading the history the device spins until *wait_flag >= wait_value,
+ * and stores *done_flag = done_value once the history has been read (both system scope, see b2s_flag_*). */
+int32_t b2s_fir_exec_hist(b2s_fir *f, const void *d_hist, size_t n_hist, const void *d_in, size_t n_in,
+                          void *d_out, size_t n_out_cap, const uint32_t *wait_flag, uint32_t wait_value,
+                          uint32_t *done_flag, uint32_t done_value, size_t *consumed, size_t *produced,
+                          int32_t *status);
 /* Same contract with host slices (pageable or pinned): chunked H2D -> kernel -> D2H pipeline
  * through an internal device ring; returns after the last D2H completed. */
 int32_t b2s_fir_filter_host(b2s_fir *f, const void *h_in, size_t n_in, void *h_out, size_t n_out_cap,
@@ -209,6 +223,21 @@ void    b2s_mavg_destroy(b2s_mavg *m);
 int32_t b2s_mavg_exec(b2s_mavg *m, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
                       size_t *consumed, size_t *produced);
 
+/* ---- fused spectrum pipe: Fft::with_options(n, Forward, fft_shift, None) -> Apply(|x|^2) ->
+ * MovingAvg<n>::new(decay_factor, history_size) [-> log10_scale * log10(.) when log10_scale != 0] of
+ * examples/spectrum/src/bin/cpu.rs:21-28 in ONE pass over the samples: 8 B/sample in, n floats per `history_size`
+ * frames out (the three separate blocks above move 32 B/sample through HBM).  Stateful like MovingAvg (avg[], i).
+ * The moving average is evaluated as a blocked scan, so values agree with the sequential f32 reference to rounding
+ * (~1e-6 relative), not bit for bit -- use b2s_fft + b2s_apply + b2s_mavg where bit equality matters.
+ * n: power of two, 32..8192.  consumed counts Complex<f32> items, produced counts f32 items. */
+typedef struct b2s_spectrum b2s_spectrum;
+int32_t b2s_spectrum_plan(b2s_ctx *ctx, size_t n, int32_t fft_shift, float decay_factor, size_t history_size,
+                          float log10_scale, b2s_spectrum **out);
+void    b2s_spectrum_destroy(b2s_spectrum *s);
+int32_t b2s_spectrum_reset(b2s_spectrum *s);
+int32_t b2s_spectrum_exec(b2s_spectrum *s, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
+                          size_t *consumed, size_t *produced);
+
 /* ---- device-resident buffer ring (≙ buffer/vulkan/{h2d,d2h}.rs + circuit.rs + slab.rs history)
  * n_slots buffers of `halo_items + chunk_items` items each stay in HBM; ownership of a slot
  * moves source-edge -> GPU block(s) -> sink-edge -> back (circuit), exactly like
@@ -237,6 +266,32 @@ int32_t b2s_slot_fetch_to_host(b2s_slot *slot, size_t items); /* async D2H into 
 int32_t b2s_slot_wait(b2s_slot *slot);             /* host wait on the slot's event            */
 size_t  b2s_ring_free_slots(const b2s_ring *r);
 size_t  b2s_ring_full_slots(const b2s_ring *r);
+/* geometry of the ring's single device allocation, for exporting it to a peer process (b2s_ipc_export):
+ * a peer addresses slot i's first data item at  peer_base + b2s_ring_slot_offset(i)  and the ring's two u32
+ * counters {ready, consumed} at  peer_base + b2s_ring_flags_offset(). */
+void   *b2s_ring_base(const b2s_ring *r);
+size_t  b2s_ring_bytes(const b2s_ring *r);
+size_t  b2s_ring_slot_offset(const b2s_ring *r, int32_t slot_index);
+size_t  b2s_ring_flags_offset(const b2s_ring *r);
+int32_t b2s_slot_index(const b2s_slot *slot);
+
+/* ---- cross-GPU plumbing of a sharded stream (no reference equivalent -- FutureSDR is single-device).
+ * One process per GPU: export a device allocation (d_base = pointer returned by b2s_malloc or b2s_ring_base) as an
+ * opaque 64-byte handle, ship the handle to the neighbour by any means (torch.distributed, a pipe), and map it
+ * there.  One process driving several GPUs uses b2s_peer_enable instead and passes raw pointers. */
+#define B2S_IPC_HANDLE_BYTES 64
+int32_t b2s_ipc_export(b2s_ctx *ctx, void *d_base, uint8_t handle[B2S_IPC_HANDLE_BYTES]);
+int32_t b2s_ipc_open(b2s_ctx *ctx, const uint8_t handle[B2S_IPC_HANDLE_BYTES], void **d_peer);
+int32_t b2s_ipc_close(b2s_ctx *ctx, void *d_peer);
+int32_t b2s_peer_enable(b2s_ctx *ctx, int32_t peer_device);
+/* Stream-ordered system-scope flags (u32 counters in device memory, local or peer):
+ * set = release store after everything queued before it; wait = the stream stalls until *flag >= value (wrap-safe),
+ * giving up after 4 s (b2s_ctx_sync then returns B2S_ETIMEOUT).  b2s_flag_read is a blocking host read. */
+int32_t b2s_flag_set(b2s_ctx *ctx, uint32_t *d_flag, uint32_t value);
+int32_t b2s_flag_wait(b2s_ctx *ctx, const uint32_t *d_flag, uint32_t value);
+int32_t b2s_flag_read(b2s_ctx *ctx, const uint32_t *d_flag, uint32_t *value);
+int32_t b2s_memcpy_d2d(b2s_ctx *ctx, void *dst, const void *src, size_t bytes); /* async, any two devices */
+int32_t b2s_memset(b2s_ctx *ctx, void *dst, int32_t byte, size_t bytes);         /* async */
 
 /* ---- tap design, host side, f64 then cast (≙ futuredsp::firdes::kaiser, firdes/basic.rs:310-459)
  * Return the tap count; write taps only if cap is large enough (call with taps=NULL to size). */

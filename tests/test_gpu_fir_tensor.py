@@ -78,8 +78,11 @@ def test_tensor_unsupported_shapes_are_refused(fb):
     with pytest.raises(fb.B200SdrError):       # decimation must divide 128 (the kept output phases are lane-static)
         fb.DecimatingFirFilter(3, np.ones(64, np.float32), algo=fb.ALGO_TENSOR)
     assert fb.DecimatingFirFilter(4, np.ones(64, np.float32), algo=fb.ALGO_TENSOR).algo == fb.ALGO_TENSOR
-    assert fb.DecimatingFirFilter(4, np.ones(52, np.float32)).algo == fb.ALGO_TENSOR      # FirBuilder::decimating(4)
-    assert fb.DecimatingFirFilter(5, np.ones(52, np.float32)).algo == fb.ALGO_DIRECT
+    ramp = lambda n: np.linspace(0.1, 1.0, n).astype(np.float32)
+    assert fb.DecimatingFirFilter(4, ramp(52)).algo == fb.ALGO_TENSOR      # FirBuilder::decimating(4)
+    assert fb.DecimatingFirFilter(5, ramp(52)).algo == fb.ALGO_DIRECT
+    # AUTO keeps CONSTANT tap vectors (boxcar / moving average) on the CUDA cores: their split-bf16 errors are coherent
+    assert fb.DecimatingFirFilter(4, np.ones(52, np.float32)).algo == fb.ALGO_DIRECT
     with pytest.raises(fb.B200SdrError):
         fb.FirFilter(np.ones(64, np.complex64), algo=fb.ALGO_TENSOR)
     with pytest.raises(fb.B200SdrError):       # < 16 taps: split-bf16 error bound too loose, refused
@@ -90,7 +93,7 @@ def test_tensor_unsupported_shapes_are_refused(fb):
     assert fb.FirFilter(np.ones(300, np.float32)).algo == fb.ALGO_FFT          # long filter: overlap-save
     assert fb.FirFilter(np.ones(300, np.float32), sample_dtype=np.float32).algo == fb.ALGO_DIRECT
     assert fb.FirFilter(np.ones(5, np.float32)).algo == fb.ALGO_DIRECT
-    assert fb.FirFilter(np.ones(256, np.float32)).algo == fb.ALGO_TENSOR
+    assert fb.FirFilter(ramp(256)).algo == fb.ALGO_TENSOR
 
 
 def test_tensor_vs_direct_full_chunk(fb):
