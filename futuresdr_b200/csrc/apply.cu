@@ -140,6 +140,14 @@ int32_t b2s_apply_exec(b2s_apply *a, const void *d_in, size_t n_in, void *d_out,
     *consumed = m; *produced = m;
     if (m == 0) return B2S_OK;
     if (!d_in || !d_out) return b2s_fail(a->ctx, B2S_EINVAL, "b2s_apply_exec: NULL buffer");
+    // the demodulators read in[j-1] while a neighbour thread writes out[j-1]: the slices must not overlap
+    // (the element-wise ops may run in place)
+    if (a->op == B2S_OP_QUAD_DEMOD || a->op == B2S_OP_QUAD_DEMOD_C32) {
+        const char *i0 = (const char *)d_in, *i1 = i0 + m * sizeof(float2);
+        const char *o0 = (const char *)d_out, *o1 = o0 + m * (a->op == B2S_OP_QUAD_DEMOD ? sizeof(float) : sizeof(float2));
+        if (i0 < o1 && o0 < i1)
+            return b2s_fail(a->ctx, B2S_EINVAL, "b2s_apply_exec: the quadrature demodulator cannot run in place (input and output overlap)");
+    }
     DeviceGuard g(a->ctx->device);
     int32_t rc = B2S_EINVAL;
     switch (a->op) {

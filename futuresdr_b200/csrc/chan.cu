@@ -16,8 +16,13 @@
 //     N-point inverse FFT is the batched FFT kernel of fft.cu (any N: radix or Bluestein), a
 //     transposing store writes channel-major output streams.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "fft_common.cuh"
+
+const float2 *b2s_fft_twiddles(const b2s_fft *p);   // fft.cu
+int b2s_fft_log2n(const b2s_fft *p);
 
 struct b2s_chan {
     b2s_ctx *ctx = nullptr;
@@ -34,6 +39,8 @@ struct b2s_chan {
     b2s_fft *ifft = nullptr;
     float2 *d_tmp = nullptr;        // 2 * tmp_items
     size_t tmp_items = 0;
+    float *d_arms_pad = nullptr;    // [TPAD][N]: d_arms zero-padded to the fused kernel's tap count
+    int tpad = 0;
 };
 
 namespace {
@@ -208,6 +215,151 @@ __global__ void chan_transpose_kernel(const float2 *__restrict__ spec, float2 *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FUSED steady state (critically sampled, N a power of two <= 256, T <= 32): FIR bank + N-point inverse FFT +
+// channel-major store in ONE kernel -- 8 B/sample in, 8 B/sample out, nothing in between touches HBM (the three
+// kernels above move 48 B/sample).  A CTA owns OB consecutive output vectors:
+//   A. the (OB + TPAD - 1) * N input samples they depend on are copied to shared memory (one contiguous span:
+//      window b receives the samples congruent to r_b mod N, so row q of the tile is in[q*N .. q*N+N));
+//   B. thread (window b, run of RL consecutive outputs) streams its column of the tile through registers ONCE:
+//      every loaded sample is multiplied into all outputs of the run that contain it (taps in registers, static
+//      indices after unrolling) -- 1 LDS.64 per ~RL*TPAD/(RL+TPAD-1) complex MACs, MAC order oldest sample first
+//      exactly like channelizer.rs:186-199;
+//   C. the OB vectors are de-spun by the Stockham passes of fft_common.cuh in shared memory (inverse = conj o FFT o conj);
+//   D. results leave transposed: for each channel the OB outputs are contiguous in its output stream.
+// Outputs whose windows still reach into the previous call's history (the first T-1 of a call) take the generic
+// three-kernel path.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LOG2N, int TPAD>
+__global__ void __launch_bounds__(256) chan_fused_kernel(const float2 *__restrict__ in, const float *__restrict__ arms_pad,
+                                                         const float2 *__restrict__ tw, float2 *__restrict__ out, int base0,
+                                                         long long o_first, long long nprod, long long out_stride) {
+    using namespace fftk;
+    constexpr int N = 1 << LOG2N;
+    constexpr int TT = (N / 16 < 1) ? 1 : N / 16;            // threads per transform
+    constexpr int OB = 256 / TT;                             // output vectors per CTA
+    constexpr int RUNS = 256 / N;                            // runs of outputs per window
+    constexpr int RL = OB / RUNS;                            // outputs per run
+    constexpr int ROWS = OB + TPAD - 1;
+    constexpr int NP = N + N / 16;
+    extern __shared__ __align__(16) unsigned char csm[];
+    float2 *X = reinterpret_cast<float2 *>(csm);             // [ROWS][N]   (reused as the transposed staging [OB][N+1])
+    constexpr size_t XCAP = ((size_t)ROWS * N > (size_t)OB * (N + 1)) ? (size_t)ROWS * N : (size_t)OB * (N + 1);
+    float2 *V = X + XCAP;                                    // [OB][NP]    FFT buffers
+    const int tid = threadIdx.x;
+    const long long o0 = o_first + (long long)blockIdx.x * OB;
+    const long long q0 = o0 - (TPAD - 1);                    // first tile row (output o uses rows o-TPAD+1 .. o); may be < 0
+    const long long n_items = nprod * N;
+
+    // ---- A: input tile (rows in front of the call only meet zero taps: zero-fill)
+    {
+        const long long base = q0 * N;
+        constexpr int TOT4 = ROWS * N / 2;                   // float4 = 2 samples
+        for (int e = tid; e < TOT4; e += 256) {
+            const long long it = base + 2ll * e;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it >= 0 && it + 1 < n_items) v = __ldg(reinterpret_cast<const float4 *>(in + it));
+            else {
+                if (it >= 0 && it < n_items) { const float2 a = __ldg(in + it); v.x = a.x; v.y = a.y; }
+                if (it + 1 >= 0 && it + 1 < n_items) { const float2 a = __ldg(in + it + 1); v.z = a.x; v.w = a.y; }
+            }
+            reinterpret_cast<float4 *>(X)[e] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- B: FIR bank
+    {
+        const int b = tid % N, run = tid / N;
+        int r = (base0 - b) % N; if (r < 0) r += N;          // window b receives samples == r (mod N)
+        int i = (b - base0 - 1) % N; if (i < 0) i += N;      // and always meets arm i (critically sampled)
+        float tap[TPAD];
+#pragma unroll
+        for (int j = 0; j < TPAD; j++) tap[j] = __ldg(arms_pad + (size_t)j * N + i);
+        float2 acc[RL];
+#pragma unroll
+        for (int u = 0; u < RL; u++) acc[u] = make_float2(0.f, 0.f);
+        const float2 *col = X + (size_t)(run * RL) * N + r;   // tile row (run*RL + k) <-> sample row o_run - TPAD + 1 + k
+#pragma unroll
+        for (int k = 0; k < RL + TPAD - 1; k++) {
+            const float2 x = col[(size_t)k * N];
+#pragma unroll
+            for (int u = 0; u < RL; u++) {
+                const int j = u + TPAD - 1 - k;              // output u sees this row as its j-th newest sample
+                if (j >= 0 && j < TPAD) { acc[u].x = fmaf(x.x, tap[j], acc[u].x); acc[u].y = fmaf(x.y, tap[j], acc[u].y); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RL; u++)                          // conjugated: the inverse transform is conj(FFT(conj(.)))
+            V[(size_t)(run * RL + u) * NP + pad(b)] = make_float2(acc[u].x, -acc[u].y);
+    }
+    __syncthreads();
+
+    // ---- C: N-point FFT of every vector; D: conjugate + transposed staging in the (now free) tile
+    {
+        const int ol = tid / TT, t = tid % TT;
+        float2 *sm = V + (size_t)ol * NP;
+        fft_passes<LOG2N, TT>([&](int idx) { return sm[pad(idx)]; },
+                              [&](int idx, float2 v) { X[(size_t)ol * (N + 1) + idx] = make_float2(v.x, -v.y); },
+                              sm, tw, t, true);
+    }
+    // (fft_passes ends with a CTA barrier)
+    for (int e = tid; e < OB * N; e += 256) {
+        const int ch = e / OB, ol = e % OB;
+        if (o0 + ol < nprod) out[(long long)ch * out_stride + o0 + ol] = X[(size_t)ol * (N + 1) + ch];
+    }
+}
+
+template <int LOG2N, int TPAD> constexpr size_t chan_fused_smem() {
+    constexpr int N = 1 << LOG2N;
+    constexpr int TT = (N / 16 < 1) ? 1 : N / 16;
+    constexpr int OB = 256 / TT;
+    constexpr size_t xcap = ((size_t)(OB + TPAD - 1) * N > (size_t)OB * (N + 1)) ? (size_t)(OB + TPAD - 1) * N : (size_t)OB * (N + 1);
+    return (xcap + (size_t)OB * (N + N / 16)) * sizeof(float2);
+}
+
+template <int LOG2N, int TPAD>
+int32_t chan_fused_launch(b2s_chan *c, const float2 *in, float2 *out, long long o_first, long long nprod, long long out_stride) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int TT = (N / 16 < 1) ? 1 : N / 16;
+    constexpr int OB = 256 / TT;
+    constexpr size_t smem = chan_fused_smem<LOG2N, TPAD>();
+    auto kern = chan_fused_kernel<LOG2N, TPAD>;
+    static PerDeviceOnce optin;
+    if (smem > 48 * 1024 && optin.need(c->ctx->device)) {
+        B2S_CUDA(c->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        optin.done(c->ctx->device);
+    }
+    const unsigned grid = (unsigned)ceil_div((size_t)(nprod - o_first), (size_t)OB);
+    kern<<<grid, 256, smem, c->ctx->stream>>>(in, c->d_arms_pad, b2s_fft_twiddles(c->ifft), out, (int)c->base_index, o_first,
+                                             nprod, out_stride);
+    B2S_CHECK_LAUNCH(c->ctx);
+    return B2S_OK;
+}
+
+template <int TPAD>
+int32_t chan_fused_dispatch(b2s_chan *c, int log2n, const float2 *in, float2 *out, long long o_first, long long nprod,
+                            long long out_stride) {
+    switch (log2n) {
+        case 2: return chan_fused_launch<2, TPAD>(c, in, out, o_first, nprod, out_stride);
+        case 3: return chan_fused_launch<3, TPAD>(c, in, out, o_first, nprod, out_stride);
+        case 4: return chan_fused_launch<4, TPAD>(c, in, out, o_first, nprod, out_stride);
+        case 5: return chan_fused_launch<5, TPAD>(c, in, out, o_first, nprod, out_stride);
+        case 6: return chan_fused_launch<6, TPAD>(c, in, out, o_first, nprod, out_stride);
+        case 7: return chan_fused_launch<7, TPAD>(c, in, out, o_first, nprod, out_stride);
+        case 8: return chan_fused_launch<8, TPAD>(c, in, out, o_first, nprod, out_stride);
+    }
+    return B2S_EAGAIN;
+}
+
+// TPAD (8 / 16 / 32) the fused kernel would use for this plan, 0 if the plan is outside its shapes
+int chan_fused_tpad(const b2s_chan *c) {
+    const int l2 = b2s_fft_log2n(c->ifft);
+    if (getenv("B2S_CHAN_NO_FUSED")) return 0;
+    if (l2 < 2 || l2 > 8 || c->D != c->N || c->T > 32) return 0;
+    return c->T <= 8 ? 8 : (c->T <= 16 ? 16 : 32);
+}
+
 }  // namespace
 
 extern "C" {
@@ -247,6 +399,16 @@ int32_t b2s_chan_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps, 
     B2S_CUDA(ctx, cudaMemcpyAsync(c->d_arms, arms.data(), arms.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     B2S_CUDA(ctx, cudaMemcpyAsync(c->d_wstate, ws.data(), ws.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     B2S_CUDA(ctx, cudaMemsetAsync(c->d_circ, 0, N * 2 * T * sizeof(float2), ctx->stream));
+    c->tpad = chan_fused_tpad(c);
+    std::vector<float> apad;
+    if (c->tpad) {
+        apad.assign((size_t)c->tpad * N, 0.0f);                                  // taps beyond T are zero (older samples)
+        std::copy(arms.begin(), arms.end(), apad.begin());
+        if (cudaMalloc((void **)&c->d_arms_pad, apad.size() * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError(); b2s_chan_destroy(c); return b2s_fail(ctx, B2S_ENOMEM, "channelizer buffers");
+        }
+        B2S_CUDA(ctx, cudaMemcpyAsync(c->d_arms_pad, apad.data(), apad.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = c;
     return B2S_OK;
@@ -262,6 +424,7 @@ void b2s_chan_destroy(b2s_chan *c) {
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_wstate) cudaFree(c->d_wstate);
     if (c->d_tmp) cudaFree(c->d_tmp);
+    if (c->d_arms_pad) cudaFree(c->d_arms_pad);
     delete c;
 }
 
@@ -306,8 +469,23 @@ int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, s
     if (nprod > n_out_cap) nprod = n_out_cap;                                  // :155-158
     if (nprod == 0) return B2S_OK;
     if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_chan_exec: NULL buffer");
+    // the first T-1 output vectors of a call still reach into the previous call's history: generic path; the rest
+    // (windows entirely inside this call's input) go through the fused kernel
+    const bool fused_ok = c->tpad && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;      // the tile copy uses 16-byte loads
+    const size_t n_generic = fused_ok ? std::min<size_t>(nprod, (size_t)T - 1) : nprod;
+    NvtxRange nvtx("b2s_chan_exec");
+    if (n_generic < nprod) {
+        int32_t rc = B2S_EAGAIN;
+        const int l2 = b2s_fft_log2n(c->ifft);
+        if (c->tpad == 8) rc = chan_fused_dispatch<8>(c, l2, in, (float2 *)d_out, (long long)n_generic, (long long)nprod, (long long)out_stride);
+        else if (c->tpad == 16) rc = chan_fused_dispatch<16>(c, l2, in, (float2 *)d_out, (long long)n_generic, (long long)nprod, (long long)out_stride);
+        else if (c->tpad == 32) rc = chan_fused_dispatch<32>(c, l2, in, (float2 *)d_out, (long long)n_generic, (long long)nprod, (long long)out_stride);
+        if (rc != B2S_OK) return rc == B2S_EAGAIN ? b2s_fail(ctx, B2S_ESTATE, "channelizer: fused shape mismatch") : rc;
+    }
+    const size_t nprod_all = nprod;
+    nprod = n_generic;
     const size_t items = nprod * N;
-    if (c->tmp_items < items) {
+    if (items && c->tmp_items < items) {
         B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (c->d_tmp) cudaFree(c->d_tmp);
         c->tmp_items = items * 5 / 4 + 1024;
@@ -315,6 +493,7 @@ int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, s
         if (e != cudaSuccess) { c->d_tmp = nullptr; c->tmp_items = 0; cudaGetLastError(); return b2s_fail(ctx, B2S_ENOMEM, "channelizer workspace"); }
     }
     float2 *bank = c->d_tmp, *spec = c->d_tmp + c->tmp_items;
+    if (items) {
     {
         const int th = (int)std::min<size_t>(128, round_up(N, 32));
         const unsigned gx = (unsigned)ceil_div(N, (size_t)th);
@@ -332,6 +511,8 @@ int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, s
     dim3 tg((unsigned)ceil_div(nprod, (size_t)32), (unsigned)ceil_div((size_t)N, (size_t)32));
     chan_transpose_kernel<<<tg, dim3(32, 8), 0, ctx->stream>>>(spec, (float2 *)d_out, N, (long long)nprod, (long long)out_stride);
     B2S_CHECK_LAUNCH(ctx);
+    }
+    nprod = nprod_all;
     const long long npush = (long long)nprod * D;
     chan_hist_update<<<N, 64, T * sizeof(float2), ctx->stream>>>(c->d_hist, in, N, T, (int)c->base_index, npush);
     B2S_CHECK_LAUNCH(ctx);

@@ -34,9 +34,14 @@ struct b2s_ctx {
     // device status word (bit0: a cross-GPU flag wait timed out); checked by b2s_ctx_sync when flag_ops > 0
     unsigned *d_status = nullptr;
     uint64_t flag_ops = 0;
-    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE, and a process may hold contexts on several:
-    // opt-in state lives here, one bit per kernel family (fir_direct.cu, fft.cu)
-    uint32_t smem_optin_done = 0;
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE and a process may hold contexts on several: a
+// `static PerDeviceOnce` next to each kernel instantiation remembers which devices have been opted in.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0; }
+    void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
 };
 
 extern thread_local std::string g_b2s_last_error;

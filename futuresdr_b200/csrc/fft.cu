@@ -148,10 +148,10 @@ int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
     constexpr size_t smem = (size_t)FPB * (N + N / 16) * sizeof(float2);
     auto kern = fft_kernel<LOG2N>;
     if (smem > 48 * 1024) {
-        static thread_local bool set = false;
-        if (!set) {
+        static PerDeviceOnce optin;              // per template instantiation, per device
+        if (optin.need(p->ctx->device)) {
             B2S_CUDA(p->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
+            optin.done(p->ctx->device);
         }
     }
     const unsigned grid = (unsigned)ceil_div((size_t)a.nfft, (size_t)FPB);
@@ -224,10 +224,10 @@ int32_t launch_bluestein(b2s_fft *p, const BsArgs &a, cudaStream_t stream) {
     constexpr size_t smem = (size_t)FPB * (M + M / 16) * sizeof(float2);
     auto kern = bluestein_kernel<LOG2M>;
     if (smem > 48 * 1024) {
-        static thread_local bool set = false;
-        if (!set) {
+        static PerDeviceOnce optin;              // per template instantiation, per device
+        if (optin.need(p->ctx->device)) {
             B2S_CUDA(p->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
+            optin.done(p->ctx->device);
         }
     }
     const unsigned grid = (unsigned)ceil_div((size_t)a.nfft, (size_t)FPB);
@@ -237,6 +237,10 @@ int32_t launch_bluestein(b2s_fft *p, const BsArgs &a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// plan internals for the kernels that embed an N-point transform (chan.cu's fused channelizer)
+const float2 *b2s_fft_twiddles(const b2s_fft *p) { return p ? p->d_tw : nullptr; }
+int b2s_fft_log2n(const b2s_fft *p) { return (p && !p->bluestein) ? p->log2n : -1; }
 
 extern "C" {
 

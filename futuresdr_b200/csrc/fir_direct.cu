@@ -467,11 +467,11 @@ int32_t launch_typed(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, siz
         return B2S_OK;
     }
     auto kern = fir_direct_kernel<S, T, kR, kThreads>;
-    static thread_local bool attr_set = false;   // per template instantiation + thread
-    if (!attr_set) {
+    static PerDeviceOnce optin;                  // per template instantiation, per device
+    if (optin.need(ctx->device)) {
         B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemBudget));
-        attr_set = true;
+        optin.done(ctx->device);
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
     const unsigned grid = (unsigned)ceil_div(n_out, (size_t)TK);

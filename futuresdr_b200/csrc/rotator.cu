@@ -9,36 +9,89 @@
 // runs it once per call (plain f32 ops, no contraction) and records the phase every 8 samples
 // (1 byte/sample of extra traffic); on the device each thread re-derives its sample's phase from
 // the record with the same IEEE operations (__fmul_rn/__fsub_rn/__fadd_rn) -- bit-identical
-// phases, data-parallel rotation.  Throughput is bounded by the host replay (~3 ns/sample).
+// phases, data-parallel rotation.  The replay runs AHEAD of the stream on a worker thread (below), so a call only
+// waits for it when the stream is sustained above the replay rate (~0.4 Gsamples/s of rotator input).
 #include <cmath>
+#include <condition_variable>
+#include <thread>
 
 #include "common.cuh"
 
 namespace {
-constexpr int kRotSub = 8;       // samples per recorded phase
+constexpr int kRotSub = 8;                      // samples per recorded phase
+constexpr size_t kRingRecs = 4u << 20;          // run-ahead window: 4 Mi records = 32 Mi samples (32 MiB pinned)
+constexpr size_t kBatchRecs = 1u << 14;         // the worker publishes its progress every 16 Ki records
 }
 
+// The recurrence is data-independent, so a WORKER THREAD runs it ahead of the stream: it fills a pinned ring with the
+// phase before every 8th sample of the (infinite) stream and an exec call only waits if the stream has outrun it
+// (sustained ~0.4 Gsamples/s, the speed of the dependent f32 multiply-add chain on one core -- the same chain the
+// reference's own rotate() runs); the records of a call travel with one or two async H2D copies.
 struct b2s_rotator {
     b2s_ctx *ctx = nullptr;
     float incr[2] = {1.f, 0.f};
-    float phase[2] = {1.f, 0.f};                 // host-side state (rotator.rs:10)
-    float2 *h_recs = nullptr, *d_recs = nullptr; // phase before sample 8*i of the current call
-    size_t recs_cap = 0;
+    float2 *h_ring = nullptr;                    // pinned, kRingRecs records; record r lives at r % kRingRecs
+    float2 *d_recs = nullptr;                    // records of the calls in flight on the device (two halves)
+    size_t d_cap = 0;
+    int half = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};      // H2D of half i done -> its ring span may be overwritten
+    uint64_t span_end[2] = {0, 0};               // one past the last record each half's copy read
+    uint64_t pos = 0;                            // samples rotated so far (stream position)
+    // worker
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t produced = 0;                       // records computed (absolute)
+    uint64_t released = 0;                       // records below this may be overwritten
+    uint64_t epoch = 0;                          // bumped by reset
+    bool quit = false;
 };
 
 namespace {
+
+void rotator_worker(b2s_rotator *r) {
+    uint64_t epoch = ~0ull, next = 0;
+    float pr = 1.f, pi = 0.f;
+    const float ir = r->incr[0], ii = r->incr[1];
+    for (;;) {
+        uint64_t limit;
+        {
+            std::unique_lock<std::mutex> lk(r->mu);
+            r->cv.wait(lk, [&] { return r->quit || r->epoch != epoch || r->produced < r->released + kRingRecs; });
+            if (r->quit) return;
+            if (r->epoch != epoch) { epoch = r->epoch; next = 0; pr = 1.f; pi = 0.f; r->produced = 0; }   // Rotator::new
+            limit = std::min<uint64_t>(r->released + kRingRecs, next + kBatchRecs);
+        }
+        // host replay of the recurrence: plain binary32 SSE operations (host code is built with -ffp-contract=off and
+        // without -ffast-math, so every product and sum is rounded separately) -- rotator.rs:26, num_complex Mul
+        for (; next < limit; next++) {
+            r->h_ring[next % kRingRecs] = make_float2(pr, pi);
+            for (int k = 0; k < kRotSub; k++) {
+                const float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;
+                pr = a - b; pi = c + d;
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(r->mu);
+            if (r->epoch == epoch) r->produced = next;
+        }
+        r->cv.notify_all();
+    }
+}
 
 __device__ __forceinline__ float2 cmul_rn(float2 a, float2 b) {       // num_complex Mul, un-fused
     return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
                        __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
 }
 
+// sample s of the call is sample (off + s) of the record span: record (off + s) / 8, then (off + s) % 8 + 1 steps
 __global__ void rotator_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
-                               const float2 *__restrict__ recs, float2 incr, long long n) {
+                               const float2 *__restrict__ recs, float2 incr, long long n, int off) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
-        float2 p = recs[s / kRotSub];
-        const int j = (int)(s % kRotSub);
+        const long long a = s + off;
+        float2 p = recs[a / kRotSub];
+        const int j = (int)(a % kRotSub);
 #pragma unroll
         for (int i = 0; i < kRotSub; i++)
             if (i <= j) p = cmul_rn(p, incr);                          // phase *= phase_incr, (j+1) times
@@ -52,11 +105,18 @@ extern "C" {
 
 int32_t b2s_rotator_create(b2s_ctx *ctx, float phase_incr, b2s_rotator **out) {
     if (!ctx || !out) return b2s_fail(ctx, B2S_EINVAL, "b2s_rotator_create: NULL argument");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
     b2s_rotator *r = new b2s_rotator();
     r->ctx = ctx;
     // Complex32::from_polar(1.0, phase_incr) = (1.0 * cos, 1.0 * sin) in f32 (rotator.rs:17)
     r->incr[0] = 1.0f * std::cos(phase_incr);
     r->incr[1] = 1.0f * std::sin(phase_incr);
+    if (cudaHostAlloc((void **)&r->h_ring, kRingRecs * sizeof(float2), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError(); delete r; return b2s_fail(ctx, B2S_ENOMEM, "rotator: pinned record ring");
+    }
+    for (int i = 0; i < 2; i++) B2S_CUDA(ctx, cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming));
+    r->worker = std::thread(rotator_worker, r);
     *out = r;
     return B2S_OK;
 }
@@ -64,15 +124,24 @@ int32_t b2s_rotator_create(b2s_ctx *ctx, float phase_incr, b2s_rotator **out) {
 void b2s_rotator_destroy(b2s_rotator *r) {
     if (!r) return;
     DeviceGuard g(r->ctx->device);
+    { std::lock_guard<std::mutex> lk(r->mu); r->quit = true; }
+    r->cv.notify_all();
+    if (r->worker.joinable()) r->worker.join();
     cudaStreamSynchronize(r->ctx->stream);
+    for (int i = 0; i < 2; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
     if (r->d_recs) cudaFree(r->d_recs);
-    if (r->h_recs) cudaFreeHost(r->h_recs);
+    if (r->h_ring) cudaFreeHost(r->h_ring);
     delete r;
 }
 
 int32_t b2s_rotator_reset(b2s_rotator *r) {
     if (!r) return b2s_fail(nullptr, B2S_EINVAL, "rotator is NULL");
-    r->phase[0] = 1.0f; r->phase[1] = 0.0f;
+    DeviceGuard g(r->ctx->device);
+    // copies of the old sequence may still be reading the ring
+    B2S_CUDA(r->ctx, cudaStreamSynchronize(r->ctx->stream));
+    { std::lock_guard<std::mutex> lk(r->mu); r->epoch++; r->produced = 0; r->released = 0; }
+    r->cv.notify_all();
+    r->pos = 0; r->span_end[0] = r->span_end[1] = 0;
     return B2S_OK;
 }
 
@@ -89,32 +158,61 @@ int32_t b2s_rotator_exec(b2s_rotator *r, const void *d_in, size_t n_in, void *d_
     if (n == 0) return B2S_OK;
     if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_rotator_exec: NULL buffer");
     DeviceGuard g(ctx->device);
-    const size_t nrec = ceil_div(n, (size_t)kRotSub);
-    B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // previous call's records may still be in flight
-    if (r->recs_cap < nrec) {
+    NvtxRange nvtx("b2s_rotator_exec");
+    // pieces of at most a quarter of the ring, so that the worker can keep running ahead while a piece is in flight
+    const size_t piece_max = (kRingRecs / 4) * kRotSub;
+    const size_t d_need = std::min(n, piece_max) / kRotSub + 2;
+    if (r->d_cap < d_need) {
+        B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (r->d_recs) cudaFree(r->d_recs);
-        if (r->h_recs) cudaFreeHost(r->h_recs);
-        r->recs_cap = nrec * 5 / 4 + 16;
-        B2S_CUDA(ctx, cudaMalloc((void **)&r->d_recs, r->recs_cap * sizeof(float2)));
-        B2S_CUDA(ctx, cudaHostAlloc((void **)&r->h_recs, r->recs_cap * sizeof(float2), cudaHostAllocDefault));
+        r->d_recs = nullptr; r->d_cap = 0;
+        B2S_CUDA(ctx, cudaMalloc((void **)&r->d_recs, 2 * d_need * sizeof(float2)));
+        r->d_cap = d_need;
     }
-    // host replay of the recurrence: plain binary32 SSE operations (host code is built with
-    // -ffp-contract=off and without -ffast-math, so every product and sum is rounded separately)
-    float pr = r->phase[0], pi = r->phase[1];
-    const float ir = r->incr[0], ii = r->incr[1];
-    for (size_t s = 0; s < n; s++) {
-        if ((s % kRotSub) == 0) r->h_recs[s / kRotSub] = make_float2(pr, pi);
-        const float a = pr * ir, b = pi * ii, c = pr * ii, d = pi * ir;
-        const float nr = a - b, ni = c + d;
-        pr = nr; pi = ni;
+    size_t done = 0;
+    while (done < n) {
+        const size_t m = std::min(n - done, piece_max);
+        const uint64_t a0 = r->pos, a1 = r->pos + m;               // absolute samples [a0, a1)
+        const uint64_t rec0 = a0 / kRotSub, rec1 = (a1 - 1) / kRotSub + 1;
+        const int h = r->half;
+        // (the device half we are about to overwrite was last read by the kernel two pieces ago: stream order covers it)
+        // Ring space: once the H2D of an earlier piece has completed, the records below that piece's start are free.
+        // Poll first; block on the event only if the worker is actually starved for space.
+        auto harvest = [&](int hh, bool block) -> int32_t {
+            if (!r->span_end[hh]) return B2S_OK;
+            cudaError_t e = block ? cudaEventSynchronize(r->ev[hh]) : cudaEventQuery(r->ev[hh]);
+            if (e == cudaErrorNotReady) { cudaGetLastError(); return B2S_OK; }
+            B2S_CUDA(ctx, e);
+            { std::lock_guard<std::mutex> lk(r->mu); r->released = std::max(r->released, r->span_end[hh]); }
+            r->span_end[hh] = 0;
+            r->cv.notify_all();
+            return B2S_OK;
+        };
+        for (int hh = 0; hh < 2; hh++) { const int32_t rc = harvest(hh, false); if (rc) return rc; }
+        for (;;) {
+            std::unique_lock<std::mutex> lk(r->mu);                  // only blocks when the stream outran the worker
+            if (r->produced >= rec1) break;
+            if (r->released + kRingRecs >= rec1) { r->cv.wait(lk, [&] { return r->produced >= rec1; }); break; }
+            lk.unlock();                                             // the worker is out of ring space: wait for a copy
+            for (int hh = 0; hh < 2; hh++) { const int32_t rc = harvest(hh, true); if (rc) return rc; }
+            std::lock_guard<std::mutex> lk2(r->mu);
+            if (r->released + kRingRecs < rec1) return b2s_fail(ctx, B2S_ESTATE, "rotator: record ring accounting");
+        }
+        float2 *drec = r->d_recs + (size_t)h * r->d_cap;
+        const size_t i0 = rec0 % kRingRecs, cnt = rec1 - rec0;
+        const size_t first = std::min(cnt, kRingRecs - i0);
+        B2S_CUDA(ctx, cudaMemcpyAsync(drec, r->h_ring + i0, first * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        if (cnt > first)
+            B2S_CUDA(ctx, cudaMemcpyAsync(drec + first, r->h_ring, (cnt - first) * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        B2S_CUDA(ctx, cudaEventRecord(r->ev[h], ctx->stream));
+        r->span_end[h] = rec0;                                      // records below rec0 are never needed again
+        const int th = 256;
+        const unsigned grid = (unsigned)std::min<size_t>(ceil_div(m, (size_t)th), (size_t)ctx->sm_count * 16);
+        rotator_kernel<<<grid, th, 0, ctx->stream>>>((const float2 *)d_in + done, (float2 *)d_out + done, drec,
+                                                     make_float2(r->incr[0], r->incr[1]), (long long)m, (int)(a0 % kRotSub));
+        B2S_CHECK_LAUNCH(ctx);
+        r->pos = a1; r->half ^= 1; done += m;
     }
-    r->phase[0] = pr; r->phase[1] = pi;
-    B2S_CUDA(ctx, cudaMemcpyAsync(r->d_recs, r->h_recs, nrec * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-    const int th = 256;
-    const unsigned grid = (unsigned)std::min<size_t>(ceil_div(n, (size_t)th), (size_t)ctx->sm_count * 16);
-    rotator_kernel<<<grid, th, 0, ctx->stream>>>((const float2 *)d_in, (float2 *)d_out, r->d_recs,
-                                                 make_float2(ir, ii), (long long)n);
-    B2S_CHECK_LAUNCH(ctx);
     return B2S_OK;
 }
 

@@ -69,10 +69,12 @@ class ShardedFir:
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.tdtype = torch.complex64 if np.dtype(sample_dtype) == np.complex64 else torch.float32
         self.sample_dtype = np.dtype(sample_dtype)
+        if exchange == "none":              # independent replicas: every rank runs its own stream (diagnostics)
+            self.rank, self.world, exchange = 0, 1, "peer"
         if exchange == "auto":
             exchange = "peer" if (compute is None and self.device.type == "cuda") else "nccl"
         if exchange not in ("peer", "nccl"):
-            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+            raise ValueError("exchange must be 'auto', 'peer', 'nccl' or 'none'")
         self.exchange = exchange
         self.have_history = False          # becomes True after the first step of the stream
         self.step_index = 0

@@ -59,7 +59,15 @@ typedef enum {
 typedef enum {
     B2S_ALGO_AUTO   = 0,
     B2S_ALGO_DIRECT = 1, /* CUDA-core register-blocked direct form (any kind, any decimation) */
-    B2S_ALGO_TENSOR = 2, /* tcgen05 block-Toeplitz GEMM, split-bf16 (real taps, 16..257, decim divides 128) */
+    B2S_ALGO_TENSOR = 2, /* tcgen05 block-Toeplitz GEMM, split-bf16 (real taps, 16..257, decim divides 128).
+                          * Numerics: operands are split into bf16 hi + lo and three of the four partial products are
+                          * summed in FP32: ~2^-18 rms per product, worst case ~3e-5 of ||taps||_1 max|x| when EVERY
+                          * product errs the same way (constant taps on constant input -- AUTO keeps constant tap
+                          * vectors on DIRECT).  Non-finite input: a NaN/Inf sample at index i makes every output of
+                          * the 128-sample blocks whose K-range contains it non-finite (inside [i-K, i+131],
+                          * K = 128*ceil((ntaps+127)/128), a superset of the reference's [i-ntaps+1, i]); all other
+                          * outputs are unaffected and no finite output is ever wrong.  Streams that may carry
+                          * non-finite samples and need the reference's exact propagation: use B2S_ALGO_DIRECT. */
     B2S_ALGO_FFT    = 3  /* overlap-save FFT convolution (c32 samples, 64..2049 taps, decim == 1)  */
 } b2s_algo;
 
@@ -175,7 +183,9 @@ typedef enum {
 int32_t b2s_apply_create(b2s_ctx *ctx, b2s_op op, float param, b2s_apply **out);
 void    b2s_apply_destroy(b2s_apply *a);
 int32_t b2s_apply_reset(b2s_apply *a); /* closure state back to its initial value */
-/* m = min(n_in, n_out_cap) items are processed (apply.rs:109) */
+/* m = min(n_in, n_out_cap) items are processed (apply.rs:109).  Element-wise ops may run in place (d_in == d_out);
+ * the stateful demodulators (B2S_OP_QUAD_DEMOD*) need disjoint slices (B2S_EINVAL otherwise) and FINITE input
+ * (their atan2 is a finite-input polynomial: inf/inf gives NaN where libm gives +-pi/4, +-3pi/4). */
 int32_t b2s_apply_exec(b2s_apply *a, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
                        size_t *consumed, size_t *produced);
 

@@ -299,6 +299,30 @@ def test_pfbarb_parity(fb, rng, rate, nfilt, ntaps):
     assert np.max(np.abs(got2 - ref)) <= 1e-5 * arm_l1 * np.max(np.abs(x)) * 2
 
 
+@pytest.mark.parametrize("rate", [0.768, 2.3])
+def test_pfbarb_long_stream_wraps_the_periodic_schedule(fb, rng, rate, monkeypatch):
+    """The timing recurrence is periodic (2 730 668 input samples at rate 0.768, 3 647 221 at 2.3): the device indexes
+    a table of ONE period built at plan time.  A stream of > 2 periods, cut at awkward places, must give the oracle's
+    exact output count and values; so must the per-call host replay it replaces (B2S_PFBARB_NO_PERIODIC=1)."""
+    nfilt, T = 32, 8
+    taps = np.resize(orc.kaiser_lowpass(0.4 / nfilt, 0.1 / nfilt, 1e-3), nfilt * T).astype(np.float32) * nfilt
+    n = 7_600_000
+    x = _noise(rng, n)
+    ref = orc.PfbArb(rate, taps, nfilt).run(x, out_cap_per_call=1 << 24)
+    cap = int(3_100_000 * max(rate, 1.0)) + 4096
+    chunks = [1_000_003, 1_730_665, 8, 2_730_668, 1 << 30]
+    got = _pfb_run(fb, rate, taps, nfilt, x, chunks, cap)
+    assert got.size == ref.size
+    arm_l1 = max(np.sum(np.abs(taps[b::nfilt])) for b in range(nfilt))
+    tol = 1e-5 * arm_l1 * np.max(np.abs(x)) * 2
+    assert np.max(np.abs(got - ref)) <= tol
+    monkeypatch.setenv("B2S_PFBARB_NO_PERIODIC", "1")
+    got2 = _pfb_run(fb, rate, taps, nfilt, x[:3_000_000], chunks, cap)
+    monkeypatch.delenv("B2S_PFBARB_NO_PERIODIC")
+    ref2 = orc.PfbArb(rate, taps, nfilt).run(x[:3_000_000], out_cap_per_call=1 << 24)
+    assert got2.size == ref2.size and np.max(np.abs(got2 - ref2)) <= tol
+
+
 def test_pfbarb_bad_arguments(fb):
     from futuresdr_b200.blocks import PfbArbResampler
     with pytest.raises(AssertionError):

@@ -59,6 +59,19 @@ def test_channelizer_parity(rng, N, ntaps, oversample):
     _drive(rng, N, ntaps, oversample, n, [5, 3, 1000, 77, 9999, 1 << 30])   # ragged calls
 
 
+@pytest.mark.parametrize("N,T", [(128, 16), (256, 8), (64, 20), (32, 3), (16, 32), (4, 5), (256, 17)])
+def test_channelizer_fused_shapes(rng, N, T, monkeypatch):
+    """Shapes of the fused steady-state kernel (FIR bank + IFFT + transposed store in one launch: N a power of two
+    <= 256, critically sampled, T <= 32 padded to 8/16/32 taps) against the oracle, and against the generic
+    three-kernel path (B2S_CHAN_NO_FUSED=1) which must agree to rounding."""
+    n = N * 3000 + 17
+    a = _drive(np.random.default_rng(123), N, N * T - 1, 1.0, n, [N * 40 + 3, 1 << 30])
+    monkeypatch.setenv("B2S_CHAN_NO_FUSED", "1")
+    b = _drive(np.random.default_rng(123), N, N * T - 1, 1.0, n, [N * 40 + 3, 1 << 30])
+    assert a.shape == b.shape
+    assert np.max(np.abs(a - b)) <= 1e-4 * np.max(np.abs(b))
+
+
 def test_channelizer_tone_lands_in_its_channel(rng):
     import torch
     from futuresdr_b200.blocks import PfbChannelizer, WorkIo

@@ -44,6 +44,34 @@ def test_rotator_bit_exact_and_stateful(rng):
     assert (n, int(st)) == (10, 1)
 
 
+def test_rotator_long_stream_wraps_the_record_ring(rng):
+    """40 Mi samples: more than the 32 Mi-sample run-ahead ring of the rotator's worker thread, so records are
+    produced, shipped and overwritten while the stream runs; pieces start at every residue mod 8.  Bit-exact, and a
+    reset starts the sequence over."""
+    import torch
+    from futuresdr_b200.blocks import Rotator
+    n = 40 * 1024 * 1024 + 5
+    x = _noise(rng, 1 << 20)
+    xs = np.tile(x, n // x.size + 1)[:n]
+    incr = 0.0123
+    ref = orc.Rotator(incr).rotate(xs)
+    r = Rotator(incr)
+    xd = torch.from_numpy(xs).cuda()
+    out = torch.empty_like(xd)
+    pos = 0
+    for step in (3, 1 << 20, 13 * 1024 * 1024 + 1, 5, 9 * 1024 * 1024 + 6, 10 ** 10):
+        m = min(step, n - pos)
+        got_n, st = r.rotate(xd[pos:pos + m], out[pos:pos + m])
+        assert got_n == m
+        pos += m
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    r.reset()
+    got_n, st = r.rotate(xd[:100_000], out[:100_000])
+    torch.cuda.synchronize()
+    assert np.array_equal(out[:100_000].cpu().numpy(), ref[:100_000])
+
+
 @pytest.mark.parametrize("decim,offset,rate", [(4, 1000.0, 48000.0), (8, -12500.0, 250000.0), (2, 100.0, 1000.0)])
 def test_xlating_fir_block(rng, decim, offset, rate):
     import torch
