@@ -263,7 +263,7 @@ def _roofline(alg_bytes, sec, note=None):
     return r
 
 
-def host_copy_ceiling(torch, dev, h_in, h_out, reps=3):
+def host_copy_ceiling(torch, dev, h_in, h_out, reps=5):
     """What the host side can deliver: concurrent H2D + D2H of the e2e buffers with plain async copies on two
     streams (no kernel).  The e2e figure cannot exceed min(h2d, d2h) / 8 B per sample."""
     d_a = torch.empty_like(h_in, device=dev)
@@ -753,10 +753,13 @@ def run_ours(args):
     # ---- device-resident throughput (`value`): inputs already in HBM
     for _ in range(args.warmup):
         sh.step(out)
-    barrier()
+    # Nothing rank-specific may sit between the barrier and the timed loop: a 20-step region is ~5 ms, and the few
+    # milliseconds NVML takes to start on rank 0 alone used to be charged to every other rank as a wait for rank 0's
+    # first chunk (round 1's "0.155 ms per step of exchange" was exactly that).
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()
     l0 = ctx.launch_count
     ev = _events(torch, args.steps + 1)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

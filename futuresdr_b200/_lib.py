@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("B2S_LIB") or os.path.join(_HERE, "libb200sdr.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EAGAIN, EUNSUPPORTED, ESTATE, ETIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7
 INSUFFICIENT_INPUT, INSUFFICIENT_OUTPUT, BOTH_SUFFICIENT = 0, 1, 2
-F32_F32, C32_F32, C32_C32 = 0, 1, 2
+F32_F32, C32_F32, C32_C32, F64_F64 = 0, 1, 2, 3
 ALGO_AUTO, ALGO_DIRECT, ALGO_TENSOR, ALGO_FFT = 0, 1, 2, 3
 (OP_SCALE_F32, OP_SCALE_C32, OP_QUAD_DEMOD, OP_NORM_SQR, OP_QUAD_DEMOD_C32, OP_EXP_F32,
  OP_MAG_C32, OP_LOG10_F32) = range(8)
@@ -44,13 +44,14 @@ SIGNATURES = {
     "b2s_fir_plan_f32_f32": (_i32, [_vp, _f32p, _sz, _sz, _vpp]),
     "b2s_fir_plan_c32_f32": (_i32, [_vp, _f32p, _sz, _sz, _vpp]),
     "b2s_fir_plan_c32_c32": (_i32, [_vp, _f32p, _sz, _sz, _vpp]),
+    "b2s_fir_plan_f64_f64": (_i32, [_vp, C.POINTER(C.c_double), _sz, _sz, _vpp]),
     "b2s_fir_destroy": (None, [_vp]),
     "b2s_fir_length": (_sz, [_vp]),
     "b2s_fir_set_algo": (_i32, [_vp, C.c_int]),
     "b2s_fir_get_algo": (_i32, [_vp]),
     "b2s_fir_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp, _i32p]),
     "b2s_fir_filter_host": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp, _i32p]),
-    "b2s_fir_exec_hist": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, C.c_uint32, _vp, C.c_uint32, _szp, _szp, _i32p]),
+    "b2s_fir_exec_hist": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _szp, _szp, _i32p]),
     "b2s_resamp_plan": (_i32, [_vp, C.c_int, _f32p, _sz, _sz, _sz, _vpp]),
     "b2s_resamp_destroy": (None, [_vp]),
     "b2s_resamp_length": (_sz, [_vp]),
@@ -117,6 +118,13 @@ SIGNATURES = {
     "b2s_firdes_kaiser_lowpass": (_sz, [C.c_double, C.c_double, C.c_double, _f32p, _sz]),
     "b2s_firdes_kaiser_multirate": (_sz, [_sz, _sz, _sz, C.c_double, _f32p, _sz]),
 }
+
+
+class Handshake(C.Structure):
+    """b2s_handshake (include/b200sdr.h): the cross-GPU flags of one b2s_fir_exec_hist call."""
+    _fields_ = [("publish_flag", C.c_void_p), ("publish_value", C.c_uint32),
+                ("wait_flag", C.c_void_p), ("wait_value", C.c_uint32),
+                ("done_flag", C.c_void_p), ("done_value", C.c_uint32)]
 
 
 class B200SdrError(RuntimeError):

@@ -181,6 +181,7 @@ int32_t b2s_fir_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntap
     *out = nullptr;
     if (ntaps == 0) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan: ntaps must be > 0");
     if (decim == 0) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan: decim must be > 0");
+    if (kind == B2S_F64_F64) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan: f64 taps are passed through b2s_fir_plan_f64_f64");
     if (kind != B2S_F32_F32 && kind != B2S_C32_F32 && kind != B2S_C32_C32)
         return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan: bad kind %d", (int)kind);
     if (ntaps > (1u << 20) || decim > (1u << 16))
@@ -193,6 +194,21 @@ int32_t b2s_fir_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntap
     if (rc != B2S_OK) { b2s_fir_destroy(f); return rc; }
     resolve_algo(f);
     rc = prepare_algo(f);
+    if (rc != B2S_OK) { b2s_fir_destroy(f); return rc; }
+    *out = f;
+    return B2S_OK;
+}
+int32_t b2s_fir_plan_f64_f64(b2s_ctx *ctx, const double *taps, size_t ntaps, size_t decim, b2s_fir **out) {
+    if (!ctx || !out || !taps) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan_f64_f64: NULL argument");
+    *out = nullptr;
+    if (ntaps == 0) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan: ntaps must be > 0");
+    if (decim == 0) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_plan: decim must be > 0");
+    if (ntaps > (1u << 20) || decim > (1u << 16)) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fir_plan: ntaps/decim too large");
+    DeviceGuard g(ctx->device);
+    b2s_fir *f = new b2s_fir();
+    f->ctx = ctx; f->kind = B2S_F64_F64; f->ntaps = ntaps; f->decim = decim;
+    f->algo_req = f->algo = B2S_ALGO_DIRECT;
+    const int32_t rc = fir_f64_prepare(f, taps);
     if (rc != B2S_OK) { b2s_fir_destroy(f); return rc; }
     *out = f;
     return B2S_OK;
@@ -213,6 +229,7 @@ void b2s_fir_destroy(b2s_fir *f) {
     cudaStreamSynchronize(f->ctx->stream);
     fir_tc_release(f);
     fir_fft_release(f);
+    fir_f64_release(f);
     if (f->d_ptaps) cudaFree(f->d_ptaps);
     delete f;
 }
@@ -221,6 +238,9 @@ size_t b2s_fir_length(const b2s_fir *f) { return f ? f->ntaps : 0; }
 
 int32_t b2s_fir_set_algo(b2s_fir *f, b2s_algo algo) {
     if (!f) return b2s_fail(nullptr, B2S_EINVAL, "fir is NULL");
+    if (f->kind == B2S_F64_F64)
+        return algo == B2S_ALGO_AUTO || algo == B2S_ALGO_DIRECT ? B2S_OK
+               : b2s_fail(f->ctx, B2S_EUNSUPPORTED, "f64 filters only have the CUDA-core form");
     if (algo == B2S_ALGO_TENSOR && !fir_tc_supported(f))
         return b2s_fail(f->ctx, B2S_EUNSUPPORTED,
                         "tensor algorithm needs real taps, 16..257 of them, and a decimation that divides 128 (kind %d, ntaps %zu, decim %zu)",
@@ -252,6 +272,7 @@ static void fir_counts(const b2s_fir *f, size_t n_in, size_t n_out_cap, size_t *
 
 static int32_t fir_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                           cudaStream_t stream) {
+    if (f->kind == B2S_F64_F64) return fir_f64_launch(f, d_in, n_in, d_out, n_out, stream);
     if (f->algo == B2S_ALGO_TENSOR) return fir_tc_launch(f, d_in, n_in, d_out, n_out, stream);
     if (f->algo == B2S_ALGO_FFT) return fir_fft_launch(f, d_in, n_in, d_out, n_out, stream);
     return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);
@@ -357,8 +378,7 @@ int32_t b2s_fir_filter_host(b2s_fir *f, const void *h_in, size_t n_in, void *h_o
 
 // ≙ Filter::filter on the logical slice  hist[0..n_hist) ++ in[0..n_in)  (include/b200sdr.h).
 int32_t b2s_fir_exec_hist(b2s_fir *f, const void *d_hist, size_t n_hist, const void *d_in, size_t n_in,
-                          void *d_out, size_t n_out_cap, const uint32_t *wait_flag, uint32_t wait_value,
-                          uint32_t *done_flag, uint32_t done_value, size_t *consumed, size_t *produced,
+                          void *d_out, size_t n_out_cap, const b2s_handshake *hs, size_t *consumed, size_t *produced,
                           int32_t *status) {
     if (!f || !consumed || !produced || !status)
         return b2s_fail(f ? f->ctx : nullptr, B2S_EINVAL, "b2s_fir_exec_hist: NULL argument");
@@ -367,28 +387,35 @@ int32_t b2s_fir_exec_hist(b2s_fir *f, const void *d_hist, size_t n_hist, const v
     fir_counts(f, n_hist + n_in, n_out_cap, consumed, produced, status);
     DeviceGuard g(ctx->device);
     cudaStream_t st = ctx->stream;
-    auto handshake_only = [&]() -> int32_t {      // nothing to compute: still honour the flag protocol
-        if (wait_flag) { int32_t rc = peer_flag_wait_launch(ctx, wait_flag, wait_value, st); if (rc) return rc; }
-        if (done_flag) return peer_flag_set_launch(ctx, done_flag, done_value, st);
-        return B2S_OK;
-    };
-    if (*produced == 0) return handshake_only();
-    if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_exec_hist: NULL buffer");
     FirHist h;
     h.d_hist = d_hist; h.n_hist = n_hist;
-    h.wait_flag = wait_flag; h.wait_value = wait_value; h.done_flag = done_flag; h.done_value = done_value;
-    if (f->algo == B2S_ALGO_TENSOR && n_hist) {
-        const int32_t rc = fir_tc_launch_hist(f, &h, d_in, n_in, d_out, *produced, st);   // fused: the loader fetches hist
+    if (hs) {
+        h.publish_flag = hs->publish_flag; h.publish_value = hs->publish_value;
+        h.wait_flag = hs->wait_flag; h.wait_value = hs->wait_value;
+        h.done_flag = hs->done_flag; h.done_value = hs->done_value;
+    }
+    // the flag protocol with separate (one-thread) kernels, for everything but the fused tensor launch
+    auto publish = [&]() -> int32_t { return h.publish_flag ? peer_flag_set_launch(ctx, h.publish_flag, h.publish_value, st) : B2S_OK; };
+    auto wait = [&]() -> int32_t { return h.wait_flag ? peer_flag_wait_launch(ctx, h.wait_flag, h.wait_value, st) : B2S_OK; };
+    auto done = [&]() -> int32_t { return h.done_flag ? peer_flag_set_launch(ctx, h.done_flag, h.done_value, st) : B2S_OK; };
+    int32_t rc;
+    if (*produced == 0) {                          // nothing to compute: still honour the protocol
+        if ((rc = publish()) || (rc = wait()) || (rc = done())) return rc;
+        return B2S_OK;
+    }
+    if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_exec_hist: NULL buffer");
+    if (f->algo == B2S_ALGO_TENSOR && f->kind != B2S_F64_F64 && (n_hist || h.publish_flag)) {
+        rc = fir_tc_launch_hist(f, &h, d_in, n_in, d_out, *produced, st);   // fused: publish, wait, fetch, done in the kernel
         if (rc != B2S_EAGAIN) return rc;
     }
     // every other path wants one contiguous slice: install the history in the n_hist items in front of d_in (the
     // caller guarantees they are writable scratch of the same allocation -- a ring slot's halo region)
-    if (wait_flag) { int32_t rc = peer_flag_wait_launch(ctx, wait_flag, wait_value, st); if (rc) return rc; }
+    if ((rc = publish()) || (rc = wait())) return rc;
     const size_t isz = kind_in_bytes(f->kind);
     char *dst = (char *)const_cast<void *>(d_in) - n_hist * isz;
     if (n_hist && dst != (const char *)d_hist)
         B2S_CUDA(ctx, cudaMemcpyAsync(dst, d_hist, n_hist * isz, cudaMemcpyDefault, st));
-    if (done_flag) { int32_t rc = peer_flag_set_launch(ctx, done_flag, done_value, st); if (rc) return rc; }
+    if ((rc = done())) return rc;
     return fir_launch(f, dst, n_hist + n_in, d_out, *produced, st);
 }
 

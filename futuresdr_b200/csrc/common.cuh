@@ -85,5 +85,5 @@ static inline size_t sat_sub(size_t a, size_t b) { return a > b ? a - b : 0; }
 static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return ceil_div(a, b) * b; }
 
-static inline size_t kind_in_bytes(b2s_kind k) { return k == B2S_F32_F32 ? 4 : 8; }
+static inline size_t kind_in_bytes(b2s_kind k) { return k == B2S_F32_F32 ? 4 : 8; }   // F64_F64: 8 as well
 static inline size_t kind_tap_floats(b2s_kind k) { return k == B2S_C32_C32 ? 2 : 1; }

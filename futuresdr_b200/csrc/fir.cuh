@@ -23,6 +23,9 @@ struct b2s_fir {
     // ---- FFT overlap-save form (fir_fft.cu): H[NF] then W_NF[NF]
     float2 *d_fftH = nullptr;
     bool fft_ready = false;
+
+    // ---- f64 x f64 (fir_f64.cu): reversed taps in double precision
+    double *d_taps64 = nullptr;
 };
 
 // fir_direct.cu
@@ -40,6 +43,8 @@ int32_t resamp_slide_launch(b2s_ctx *ctx, b2s_kind kind, const float *d_gtab, si
 struct FirHist {
     const void *d_hist = nullptr;
     size_t n_hist = 0;
+    unsigned *publish_flag = nullptr;
+    unsigned publish_value = 0;
     const unsigned *wait_flag = nullptr;
     unsigned wait_value = 0;
     unsigned *done_flag = nullptr;
@@ -53,6 +58,10 @@ int32_t fir_tc_prepare(b2s_fir *f);
 int32_t fir_tc_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                       cudaStream_t stream);
 void    fir_tc_release(b2s_fir *f);
+// fir_f64.cu
+int32_t fir_f64_prepare(b2s_fir *f, const double *taps);
+int32_t fir_f64_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out, cudaStream_t stream);
+void    fir_f64_release(b2s_fir *f);
 // fir_fft.cu
 bool    fir_fft_supported(const b2s_fir *f);
 int32_t fir_fft_prepare(b2s_fir *f);

@@ -254,6 +254,8 @@ struct TcParams {
     unsigned wait_value;
     unsigned *done_flag;         // *done_flag = done_value (release, system scope) once hist sits in shared memory
     unsigned done_value;
+    unsigned *pub_flag;          // *pub_flag = pub_value (release, system scope) as soon as the kernel runs: everything queued
+    unsigned pub_value;          // before it on the stream (the chunk this rank owns) is in HBM
     unsigned *status;            // device status word of the context: bit0 = a flag wait timed out
 };
 
@@ -293,6 +295,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) fir_tc_kernel(const TcParams pr
         gen_base + kStages * kStageBytes + kRawSlots * kRawSlotBytes + kOutStages * kOutStageBytes + 8 * kNumBars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (prm.pub_flag && blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(prm.pub_flag), "r"(prm.pub_value) : "memory");
+    }
     const int DK = prm.DK, K = 128 * DK;
     const int nacc = (512 - K) / kNTile;             // accumulators that fit next to the taps (1 or 2)
     const int atoms = kAtomsOut + DK - 1;            // physical 8-row atoms per K-chunk
@@ -763,6 +769,8 @@ int32_t fir_tc_launch_hist(b2s_fir *f, const FirHist *h, const void *d_in, size_
     prm.wait_value = h ? h->wait_value : 0;
     prm.done_flag = (h && n_hist) ? h->done_flag : nullptr;
     prm.done_value = h ? h->done_value : 0;
+    prm.pub_flag = h ? h->publish_flag : nullptr;
+    prm.pub_value = h ? h->publish_value : 0;
     prm.status = ctx->d_status;
     prm.out = (float *)d_out;
     prm.g = f->d_ptaps + (size_t)f->decim * f->Upad;      // plain reversed taps (fir_direct_prepare)
@@ -776,7 +784,7 @@ int32_t fir_tc_launch_hist(b2s_fir *f, const FirHist *h, const void *d_in, size_
     prm.flags = f->tc_flags;
     prm.out_bulk = (a_out & 15) == 0 && !(f->tc_flags & 16);   // flags bit4: force per-lane stores
     const int grid = std::min(prm.num_tiles, ctx->sm_count);
-    if (prm.wait_flag || prm.done_flag) ctx->flag_ops++;
+    if (prm.wait_flag) ctx->flag_ops++;
     if (cplx) fir_tc_kernel<true><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
     else fir_tc_kernel<false><<<grid, kThreadsTC, kSmemTC, stream>>>(prm);
     B2S_CHECK_LAUNCH(ctx);

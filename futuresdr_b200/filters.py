@@ -29,6 +29,10 @@ class ComputationStatus(enum.IntEnum):
 
 
 def _kind(sample_dtype, taps: np.ndarray) -> int:
+    if np.dtype(sample_dtype) == np.float64:
+        if np.iscomplexobj(taps):
+            raise TypeError("no futuredsp impl for f64 samples with complex taps")
+        return _lib.F64_F64                                  # fir.rs:217-226
     cin = np.dtype(sample_dtype) == np.complex64
     ctap = np.iscomplexobj(taps)
     if not cin and np.dtype(sample_dtype) != np.float32:
@@ -51,7 +55,7 @@ def _buf(x, want_dtype, writable=False):
     """-> (ptr, n_items, is_device, keepalive)"""
     if _is_torch(x):
         import torch
-        td = torch.complex64 if np.dtype(want_dtype) == np.complex64 else torch.float32
+        td = {np.dtype(np.complex64): torch.complex64, np.dtype(np.float64): torch.float64}.get(np.dtype(want_dtype), torch.float32)
         if x.dtype != td:
             raise TypeError(f"expected {td}, got {x.dtype}")
         if not x.is_contiguous():
@@ -122,9 +126,14 @@ class DecimatingFirFilter(_FilterBase):
         self.sample_dtype = np.dtype(sample_dtype)
         self.decimation = int(decimation)
         kind = _kind(sample_dtype, np.asarray(taps))
-        t, tp = _taps_ptr(taps, kind)
-        check(lib.b2s_fir_plan(self.ctx.handle, kind, tp, t.size, self.decimation, C.byref(self._h)),
-              self.ctx.handle)
+        if kind == _lib.F64_F64:
+            t = np.ascontiguousarray(taps, dtype=np.float64)
+            check(lib.b2s_fir_plan_f64_f64(self.ctx.handle, t.ctypes.data_as(C.POINTER(C.c_double)), t.size,
+                                           self.decimation, C.byref(self._h)), self.ctx.handle)
+        else:
+            t, tp = _taps_ptr(taps, kind)
+            check(lib.b2s_fir_plan(self.ctx.handle, kind, tp, t.size, self.decimation, C.byref(self._h)),
+                  self.ctx.handle)
         if algo != _lib.ALGO_AUTO:
             self.set_algo(algo)
 

@@ -200,25 +200,28 @@ class ShardedFir:
         isz = self.sample_dtype.itemsize
         cur = self._cur
         d_in = self._base + self._slot_off[cur]
+        from ._lib import Handshake
+        hs = Handshake()
         if W > 1 and H:
-            check(lib.b2s_flag_set(self.ctx.handle, self._ready, t + 1), self.ctx.handle)     # publish chunk t
+            hs.publish_flag, hs.publish_value = self._ready, t + 1                            # publish chunk t
         first_of_stream = r == 0 and t == 0
         c, p, st = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
         if self.on_kernel:
             self.on_kernel("begin")
         if first_of_stream or H == 0:
-            check(lib.b2s_fir_exec(self._filter._h, C.c_void_p(d_in), S, C.c_void_p(out.data_ptr()), out.numel(),
-                                   C.byref(c), C.byref(p), C.byref(st)), self.ctx.handle)
+            check(lib.b2s_fir_exec_hist(self._filter._h, None, 0, C.c_void_p(d_in), S, C.c_void_p(out.data_ptr()),
+                                        out.numel(), C.byref(hs), C.byref(c), C.byref(p), C.byref(st)), self.ctx.handle)
         else:
             if r == 0:      # history = the tail of rank W-1's chunk of the PREVIOUS step
                 src_slot, need = (t - 1) % self.n_slots, t
             else:           # history = the tail of rank r-1's chunk of THIS step
                 src_slot, need = cur, t + 1
             d_hist = self._left_base + self._slot_off[src_slot] + (S - H) * isz
-            wf = C.c_void_p(self._left_base + self._flags_off) if W > 1 else None
-            df = C.c_void_p(self._left_base + self._flags_off + 4) if W > 1 else None
+            if W > 1:
+                hs.wait_flag, hs.wait_value = self._left_base + self._flags_off, need
+                hs.done_flag, hs.done_value = self._left_base + self._flags_off + 4, need
             check(lib.b2s_fir_exec_hist(self._filter._h, C.c_void_p(d_hist), H, C.c_void_p(d_in), S,
-                                        C.c_void_p(out.data_ptr()), out.numel(), wf, need, df, need,
+                                        C.c_void_p(out.data_ptr()), out.numel(), C.byref(hs),
                                         C.byref(c), C.byref(p), C.byref(st)), self.ctx.handle)
         if self.on_kernel:
             self.on_kernel("end")

@@ -52,7 +52,8 @@ extern "C" {
 typedef enum {
     B2S_F32_F32 = 0, /* f32 samples, f32 taps                 */
     B2S_C32_F32 = 1, /* Complex<f32> samples, f32 taps        */
-    B2S_C32_C32 = 2  /* Complex<f32> samples, Complex<f32> taps */
+    B2S_C32_C32 = 2, /* Complex<f32> samples, Complex<f32> taps */
+    B2S_F64_F64 = 3  /* f64 samples, f64 taps (fir.rs:217-226; plan with b2s_fir_plan_f64_f64) */
 } b2s_kind;
 
 /* FIR algorithm selection (no reference equivalent; AUTO picks by tap count / kind) */
@@ -112,6 +113,9 @@ int32_t b2s_fir_plan(b2s_ctx *ctx, b2s_kind kind, const float *taps, size_t ntap
 int32_t b2s_fir_plan_f32_f32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t decim, b2s_fir **out);
 int32_t b2s_fir_plan_c32_f32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t decim, b2s_fir **out);
 int32_t b2s_fir_plan_c32_c32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t decim, b2s_fir **out);
+/* f64 samples x f64 taps (fir.rs:217-226, decimating_fir.rs:117-130): plain CUDA-core form, un-fused multiply/add in
+ * tap order -- bit-identical to the stable-Rust loop; b2s_fir_exec / b2s_fir_exec_hist take f64 items. */
+int32_t b2s_fir_plan_f64_f64(b2s_ctx *ctx, const double *taps, size_t ntaps, size_t decim, b2s_fir **out);
 void    b2s_fir_destroy(b2s_fir *f);
 size_t  b2s_fir_length(const b2s_fir *f);           /* ≙ Filter::length, lib.rs:65-67 */
 int32_t b2s_fir_set_algo(b2s_fir *f, b2s_algo algo);
@@ -128,11 +132,19 @@ int32_t b2s_fir_exec(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, siz
  * loader fetches the history itself (over NVLink for peer memory): one launch, no copy, no host synchronisation.
  * Other paths copy it into the n_hist items in FRONT of d_in, which must therefore be writable scratch of the same
  * allocation (a ring slot's halo region; b2s_ring_create(..., halo_items >= n_hist, ...)).
- * Optional handshake (NULL = none): before reading the history the device spins until *wait_flag >= wait_value,
- * and stores *done_flag = done_value once the history has been read (both system scope, see b2s_flag_*). */
+ * Optional cross-GPU handshake `hs` (NULL = none; every flag pointer inside may be NULL as well), all system scope,
+ * see b2s_flag_*:  publish: *publish_flag = publish_value is stored when the call starts executing -- "my chunk
+ * (everything queued on this context before the call) is in HBM", what the right neighbour waits for;  wait: before
+ * reading the history the device spins until *wait_flag >= wait_value;  done: *done_flag = done_value is stored
+ * once the history has been read, so its owner may overwrite it.  On the tensor path all three happen INSIDE the FIR
+ * kernel (no extra launch). */
+typedef struct b2s_handshake {
+    uint32_t       *publish_flag; uint32_t publish_value;
+    const uint32_t *wait_flag;    uint32_t wait_value;
+    uint32_t       *done_flag;    uint32_t done_value;
+} b2s_handshake;
 int32_t b2s_fir_exec_hist(b2s_fir *f, const void *d_hist, size_t n_hist, const void *d_in, size_t n_in,
-                          void *d_out, size_t n_out_cap, const uint32_t *wait_flag, uint32_t wait_value,
-                          uint32_t *done_flag, uint32_t done_value, size_t *consumed, size_t *produced,
+                          void *d_out, size_t n_out_cap, const b2s_handshake *hs, size_t *consumed, size_t *produced,
                           int32_t *status);
 /* Same contract with host slices (pageable or pinned): chunked H2D -> kernel -> D2H pipeline
  * through an internal device ring; returns after the last D2H completed. */

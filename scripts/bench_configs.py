@@ -78,6 +78,42 @@ def main():
         nn = n // 4
         sec = timeit(lambda: f.filter(x[: nn + 1023], y[:nn]), iters=3, warm=1)
         report("fir_c32_1024taps_auto", nn, 16 * nn, sec, extra=f"algo={f.algo}")
+    if want("fir1024") and not want("fir"):
+        taps = rng.uniform(-1, 1, 1024).astype(np.float32)
+        f = fb.FirFilter(taps)
+        nn = n // 4
+        sec = timeit(lambda: f.filter(x[: nn + 1023], y[:nn]), iters=3, warm=1)
+        report("fir_c32_1024taps_auto", nn, 16 * nn, sec, extra=f"algo={f.algo}")
+    if want("fft4096") and not want("fft"):
+        fft = B.Fft(4096)
+        sec = timeit(lambda: fft.transform(x[:n], y[:n]))
+        report("fft_4096_fwd", n, 16 * n, sec)
+    if want("demod") and not want("chain"):
+        n4 = n // 4
+        dem = B.Apply(B.ApplyOp.QuadDemodC32)
+        z = torch.empty(n4, dtype=torch.complex64, device="cuda")
+        sec = timeit(lambda: dem.apply(y[:n4], z))
+        report("quad_demod_c32", n4, 16 * n4, sec)
+    if want("fused"):
+        # fused rows of round 2: spectrum pipe in one pass, channelizer in one launch
+        for N in (2048, 4096):
+            sp = B.SpectrumPipe(N, 0.1, 3)
+            po = torch.empty(n // 3 + 2 * N, dtype=torch.float32, device="cuda")
+            sec = timeit(lambda: sp.process(x[:n], po), iters=5, warm=2)
+            report(f"spectrum_pipe_fused_{N}", n, 8 * n + 4 * (n // 3), sec, extra="FFT + |x|^2 + MovingAvg(0.1, 3): spectrum_kernel + scan + fixup")
+        for N, T in ((64, 16), (16, 16), (256, 8)):
+            ctaps = (orc.kaiser_lowpass(0.4 / N, 0.1 / N, 1e-3)).astype(np.float32)
+            ctaps = np.resize(ctaps, N * T)
+            ch = B.PfbChannelizer(N, ctaps, 1.0)
+            ch.reserve_outputs(n // N + 8)
+            ch.input.set(x[:n])
+            ch.work(B.WorkIo())                               # window fill
+
+            def run_ch():
+                ch.input.pos, ch.produced = 0, 0
+                ch.work(B.WorkIo())
+            sec = timeit(run_ch, iters=5, warm=1)
+            report(f"pfb_channelizer_fused_{N}ch_{T}taps", n, 16 * n, sec, extra="FIR bank + IFFT + transposed store in one launch")
     if want("f32"):
         # f32 x f32 64 taps (perf/fir config-1 kernel)
         xr = torch.view_as_real(x).reshape(-1)[: 2 * n]

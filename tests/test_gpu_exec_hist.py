@@ -25,14 +25,19 @@ def _ref(taps, decim, x, cap):
     return c, p, int(st), o
 
 
-def _exec_hist(fir, hist_t, in_t, out_t, wait=None, done=None):
-    from futuresdr_b200._lib import lib, check
+def _exec_hist(fir, hist_t, in_t, out_t, wait=None, done=None, publish=None):
+    from futuresdr_b200._lib import lib, check, Handshake
     c, p, st = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
-    wf, wv = (C.c_void_p(wait[0]), wait[1]) if wait else (None, 0)
-    df, dv = (C.c_void_p(done[0]), done[1]) if done else (None, 0)
+    hs = Handshake()
+    if wait:
+        hs.wait_flag, hs.wait_value = wait
+    if done:
+        hs.done_flag, hs.done_value = done
+    if publish:
+        hs.publish_flag, hs.publish_value = publish
     check(lib.b2s_fir_exec_hist(fir._h, C.c_void_p(hist_t.data_ptr() if hist_t is not None and hist_t.numel() else 0),
                                 hist_t.numel() if hist_t is not None else 0, C.c_void_p(in_t.data_ptr()), in_t.numel(),
-                                C.c_void_p(out_t.data_ptr()), out_t.numel(), wf, wv, df, dv,
+                                C.c_void_p(out_t.data_ptr()), out_t.numel(), C.byref(hs) if (wait or done or publish) else None,
                                 C.byref(c), C.byref(p), C.byref(st)), fir.ctx.handle)
     return c.value, p.value, st.value
 
@@ -107,11 +112,14 @@ def test_exec_hist_flags_and_timeout():
     buf[256:] = torch.from_numpy(x[ntaps - 1:]).cuda()
     out = torch.zeros(n, dtype=torch.complex64, device="cuda")
     check(lib.b2s_flag_set(fir.ctx.handle, C.c_void_p(ready), 7), fir.ctx.handle)
-    c, p, st = _exec_hist(fir, hist, buf[256:], out, wait=(ready, 7), done=(consumed, 7))
+    published = flags.data_ptr() + 8
+    c, p, st = _exec_hist(fir, hist, buf[256:], out, wait=(ready, 7), done=(consumed, 7), publish=(published, 41))
     fir.ctx.sync()
     v = C.c_uint32(0)
     check(lib.b2s_flag_read(fir.ctx.handle, C.c_void_p(consumed), C.byref(v)), fir.ctx.handle)
     assert v.value == 7 and p == n
+    check(lib.b2s_flag_read(fir.ctx.handle, C.c_void_p(published), C.byref(v)), fir.ctx.handle)
+    assert v.value == 41
     _, _, _, ro = _ref(taps, 1, x, n)
     tol = 1e-5 * float(np.sum(np.abs(taps))) * float(np.max(np.abs(x)))
     assert float(np.max(np.abs(out.cpu().numpy() - ro))) <= tol

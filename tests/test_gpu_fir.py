@@ -219,3 +219,41 @@ def test_bad_arguments_fail_loudly(fb):
         fb.DecimatingFirFilter(0, [1.0, 2.0])
     with pytest.raises(TypeError):
         fb.FirFilter(np.ones(3, np.complex64), sample_dtype=np.float32)
+
+
+def test_f64_fir_bit_exact_and_known_answer(rng):
+    """The f64 x f64 Filter impl (fir.rs:217-226): the reference's f64 known-answer test (fir.rs:343-365: taps [1, 2],
+    4 in / 3 out -> (3, 3, BothSufficient)) and random data bit for bit (un-fused multiply/add in tap order), device
+    and host slices, with decimation."""
+    import torch
+    import futuresdr_b200 as fb
+    f = fb.FirFilter([1.0, 2.0], sample_dtype=np.float64)
+    o = torch.zeros(3, dtype=torch.float64, device="cuda")
+    c, p, st = f.filter(torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64, device="cuda"), o)
+    torch.cuda.synchronize()
+    assert (c, p, int(st)) == (3, 3, 2) and o.cpu().tolist() == [4.0, 7.0, 10.0]
+    for ntaps, decim in ((64, 1), (257, 1), (33, 3), (5000, 2)):
+        taps = rng.standard_normal(ntaps)
+        x = rng.standard_normal(200_000)
+        flt = fb.DecimatingFirFilter(decim, taps, sample_dtype=np.float64)
+        od = torch.zeros(x.size, dtype=torch.float64, device="cuda")
+        c, p, st = flt.filter(torch.from_numpy(x).cuda(), od)
+        torch.cuda.synchronize()
+        # oracle: orc_fir_f64_f64 (decim 1) / the same loop at stride D
+        g = taps[::-1]
+        n_ref = (x.size + 1 - ntaps) // decim
+        assert (c, p) == (n_ref * decim, n_ref)
+        if decim == 1:
+            _, _, _, ref = orc.fir_f64(taps, x, x.size)
+            assert np.array_equal(od[:p].cpu().numpy(), ref)
+        else:
+            k = rng.integers(0, n_ref, 200)
+            for kk in k:
+                s = 0.0
+                seg = x[decim - 1 + kk * decim: decim - 1 + kk * decim + ntaps]
+                for t in range(ntaps):
+                    s = s + seg[t] * g[t]
+                assert od[kk].item() == s
+        ho = np.zeros(p, np.float64)
+        c2, p2, _ = flt.filter(x, ho)
+        assert (c2, p2) == (c, p) and np.array_equal(ho, od[:p].cpu().numpy())
