@@ -507,9 +507,21 @@ def sec_config3_fm_chain(torch, fb, dev, args, h_in, h_out):
     total, S = 256 * 1024 * 1024, CHUNK
     nchunks = total // S
     H = 52                                                    # ceil(51 / 4) * 4: history keeping the decimator phase
+    # synthetic input: an FM signal (sinusoidal message, closed-form phase evaluated in f64) + white noise at
+    # -26 dB.  Pure noise would make the parity spot check meaningless: arg() jumps by 2*pi wherever a decimator output
+    # differs in the last bit near the negative real axis.
     x = torch.empty(total, dtype=torch.complex64, device=dev)
     g = torch.Generator(device=dev).manual_seed(SEED + 3)
-    torch.view_as_real(x).normal_(generator=g)
+    seg = 16 * 1024 * 1024
+    for c0 in range(0, total, seg):
+        tt = torch.arange(c0, c0 + seg, dtype=torch.float64, device=dev)
+        ph = (-(0.05 / 0.0007)) * torch.cos(2 * np.pi * 0.0007 * tt)
+        xs = torch.view_as_real(x[c0:c0 + seg])
+        xs.normal_(generator=g)
+        xs.mul_(0.05)
+        xs[:, 0] += torch.cos(ph).float()
+        xs[:, 1] += torch.sin(ph).float()
+        del tt, ph
     d1 = torch.empty(S // 4 + 16, dtype=torch.complex64, device=dev)
     d2 = torch.empty(S // 4 + 16, dtype=torch.complex64, device=dev)
     d3 = torch.empty(int(S // 4 * 0.768) + 4096, dtype=torch.complex64, device=dev)
@@ -563,7 +575,8 @@ def sec_config3_fm_chain(torch, fb, dev, args, h_in, h_out):
     torch.cuda.synchronize()
     ydev = d3[:o].cpu().numpy()
     parity = {"n_in": n_cpu, "count_match": bool(o == yref.size), "n_out": int(o),
-              "max_abs_err": float(np.max(np.abs(ydev - yref[:o]))) if o else None}
+              "max_abs_err": float(np.max(np.abs(ydev - yref[:o]))) if o else None,
+              "note": "device chain on the first 4 Mi samples of this run's input against the oracle chain; phases are O(pi)"}
     # end to end through host buffers: 64 Mi samples in 4 chunks of 16 Mi
     n_e = h_in.numel() - (h_in.numel() % 4)
     ce = 16 * 1024 * 1024

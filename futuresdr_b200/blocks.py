@@ -40,21 +40,30 @@ def _tdtype(np_dtype):
     return torch.complex64 if np.dtype(np_dtype) == np.complex64 else torch.float32
 
 
+def _ctx_device(ctx) -> torch.device:
+    """The device a block's context lives on: every port buffer of the block is allocated THERE (not on whatever
+    device happens to be current), so the pointers handed to the C ABI belong to the context's GPU."""
+    return torch.device("cuda", ctx.device) if ctx is not None else torch.device("cuda", torch.cuda.current_device())
+
+
 class Reader:
     """mocker::Reader<T> (mocker.rs:213-290): a vector that reports finished() == true."""
 
-    def __init__(self, dtype):
+    def __init__(self, dtype, device=None):
         self.dtype = np.dtype(dtype)
-        self.data = torch.zeros(0, dtype=_tdtype(dtype), device="cuda")
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.data = torch.zeros(0, dtype=_tdtype(dtype), device=self.device)
         self.pos = 0
         self._finished = True
         self.min_items = 1
 
     def set(self, data):
         if isinstance(data, torch.Tensor):
-            t = data.to(device="cuda", dtype=_tdtype(self.dtype))
+            if data.is_cuda and data.device != self.device:
+                raise ValueError(f"input slice lives on {data.device}, the block's context on {self.device}")
+            t = data.to(device=self.device, dtype=_tdtype(self.dtype))
         else:
-            t = torch.from_numpy(np.ascontiguousarray(np.asarray(data), dtype=self.dtype)).cuda()
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(data), dtype=self.dtype)).to(self.device)
         self.data, self.pos = t.contiguous(), 0
 
     def slice(self) -> torch.Tensor:
@@ -74,14 +83,15 @@ class Reader:
 class Writer:
     """mocker::Writer<T> (mocker.rs:326-400): a vector with reserved capacity."""
 
-    def __init__(self, dtype):
+    def __init__(self, dtype, device=None):
         self.dtype = np.dtype(dtype)
-        self.data = torch.zeros(0, dtype=_tdtype(dtype), device="cuda")
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.data = torch.zeros(0, dtype=_tdtype(dtype), device=self.device)
         self.len = 0
         self.min_items = 1
 
     def reserve(self, n: int):
-        self.data = torch.zeros(n, dtype=_tdtype(self.dtype), device="cuda")
+        self.data = torch.zeros(n, dtype=_tdtype(self.dtype), device=self.device)
         self.len = 0
 
     def slice(self) -> torch.Tensor:
@@ -103,8 +113,10 @@ class Block:
     out_dtype = np.complex64
 
     def _ports(self):
-        self.input = Reader(self.in_dtype)
-        self.output = Writer(self.out_dtype)
+        ctx = getattr(self, "ctx", None) or getattr(getattr(self, "filter", None), "ctx", None)
+        dev = _ctx_device(ctx)
+        self.input = Reader(self.in_dtype, dev)
+        self.output = Writer(self.out_dtype, dev)
 
     def work(self, io: WorkIo):          # pragma: no cover
         raise NotImplementedError
@@ -380,14 +392,14 @@ class PfbSynthesizer(Block):
         self._h = C.c_void_p()
         check(lib.b2s_synth_plan_c32(self.ctx.handle, self.num_channels, taps.ctypes.data_as(C.POINTER(C.c_float)),
                                      taps.size, C.byref(self._h)), self.ctx.handle)
-        self.inputs = torch.zeros(self.num_channels, 0, dtype=torch.complex64, device="cuda")
+        self.inputs = torch.zeros(self.num_channels, 0, dtype=torch.complex64, device=_ctx_device(self.ctx))
         self.in_pos = 0
         self.inputs_finished = True
-        self.output = Writer(np.complex64)
+        self.output = Writer(np.complex64, _ctx_device(self.ctx))
 
     def set_inputs(self, x):
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.complex64))
-        self.inputs = t.to(device="cuda", dtype=torch.complex64).contiguous()
+        self.inputs = t.to(device=_ctx_device(self.ctx), dtype=torch.complex64).contiguous()
         assert self.inputs.shape[0] == self.num_channels
         self.in_pos = 0
 
@@ -504,12 +516,12 @@ class PfbChannelizer(Block):
         check(lib.b2s_chan_plan_c32(self.ctx.handle, self.num_channels, taps.ctypes.data_as(C.POINTER(C.c_float)),
                                     taps.size, float(oversample_rate), C.byref(self._h)), self.ctx.handle)
         self.decimation_factor = int(lib.b2s_chan_decimation(self._h))
-        self.input = Reader(np.complex64)
-        self.outputs = torch.zeros(self.num_channels, 0, dtype=torch.complex64, device="cuda")
+        self.input = Reader(np.complex64, _ctx_device(self.ctx))
+        self.outputs = torch.zeros(self.num_channels, 0, dtype=torch.complex64, device=_ctx_device(self.ctx))
         self.produced = 0
 
     def reserve_outputs(self, n: int):
-        self.outputs = torch.zeros(self.num_channels, n, dtype=torch.complex64, device="cuda")
+        self.outputs = torch.zeros(self.num_channels, n, dtype=torch.complex64, device=_ctx_device(self.ctx))
         self.produced = 0
 
     def work(self, io: WorkIo):

@@ -106,12 +106,19 @@ __device__ __forceinline__ void fft_pass(const FftArgs &a, const float2 *gin, fl
 
 constexpr int kFftThreads = 256;
 
+// threads per CTA / CTAs per SM the register allocation must allow, per size.  8192: the unconstrained build takes
+// 171 registers = one 256-thread CTA per SM although shared memory admits three -> cap at 128 (16 B of spills), two
+// CTAs.  16384: one transform fills 139 KiB of shared memory, so one CTA per SM whatever we do -- 512 threads halve
+// the butterflies (and registers) per thread and double the warps that hide latency.
+template <int LOG2N> struct FftCfg { static constexpr int THREADS = LOG2N >= 14 ? 512 : 256, MINB = LOG2N == 13 ? 2 : 1; };
+
 template <int LOG2N>
-__global__ void __launch_bounds__(kFftThreads) fft_kernel(const FftArgs a) {
+__global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) fft_kernel(const FftArgs a) {
     constexpr int N = 1 << LOG2N;
+    constexpr int TH = FftCfg<LOG2N>::THREADS;
     using PL = Plan<LOG2N>;
-    constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > kFftThreads) ? kFftThreads : N / 16);   // threads per transform
-    constexpr int FPB = kFftThreads / T;                                                    // transforms per CTA
+    constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > TH) ? TH : N / 16);                     // threads per transform
+    constexpr int FPB = TH / T;                                                             // transforms per CTA
     constexpr int NP = N + N / 16;                                                          // padded length
     extern __shared__ __align__(16) unsigned char fsm[];
     const int t = threadIdx.x % T, fl = threadIdx.x / T;
@@ -143,8 +150,9 @@ __global__ void __launch_bounds__(kFftThreads) fft_kernel(const FftArgs a) {
 template <int LOG2N>
 int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
-    constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > kFftThreads) ? kFftThreads : N / 16);
-    constexpr int FPB = kFftThreads / T;
+    constexpr int TH = FftCfg<LOG2N>::THREADS;
+    constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > TH) ? TH : N / 16);
+    constexpr int FPB = TH / T;
     constexpr size_t smem = (size_t)FPB * (N + N / 16) * sizeof(float2);
     auto kern = fft_kernel<LOG2N>;
     if (smem > 48 * 1024) {
@@ -155,7 +163,7 @@ int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
         }
     }
     const unsigned grid = (unsigned)ceil_div((size_t)a.nfft, (size_t)FPB);
-    kern<<<grid, kFftThreads, smem, stream>>>(a);
+    kern<<<grid, TH, smem, stream>>>(a);
     B2S_CHECK_LAUNCH(p->ctx);
     return B2S_OK;
 }

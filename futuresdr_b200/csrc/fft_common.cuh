@@ -162,4 +162,28 @@ __device__ __forceinline__ void fft_passes(LoadF first_load, StoreF last_store, 
     }
 }
 
+// Same, with a hook that runs right after the first pass (its source buffer is free from then on: the caller
+// starts the asynchronous fetch of the NEXT transform's input there).  Plans with at least two passes (N >= 32).
+template <int LOG2N, int T, typename LoadF, typename HookF, typename StoreF>
+__device__ __forceinline__ void fft_passes_hook(LoadF first_load, HookF after_first, StoreF last_store, float2 *sm,
+                                                const float2 *__restrict__ tw, int t) {
+    constexpr int N = 1 << LOG2N;
+    using PL = Plan<LOG2N>;
+    static_assert(PL::P >= 2, "fft_passes_hook needs a multi-pass plan");
+    auto ld_sm = [&](int idx) { return sm[pad(idx)]; };
+    auto st_sm = [&](int idx, float2 v) { sm[pad(idx)] = v; };
+    ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, false);
+    after_first();
+    if constexpr (PL::P == 2) {
+        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, last_store, tw, t, true);
+    } else if constexpr (PL::P == 3) {
+        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
+        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, last_store, tw, t, true);
+    } else {
+        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
+        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, st_sm, tw, t, true);
+        ss_pass<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T>(ld_sm, last_store, tw, t, true);
+    }
+}
+
 }  // namespace fftk

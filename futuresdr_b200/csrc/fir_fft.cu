@@ -11,6 +11,7 @@
 // cores).  Radix-16 Stockham passes from fft_common.cuh; H is computed in f64 on the host.
 // Parity: |err| <~ 1e-6 * rms(y) * sqrt(log2 NF), far inside 1e-5 * ||taps||_1 * max|x|.
 #include <cmath>
+#include <cstdlib>
 
 #include "fft_common.cuh"
 #include "fir.cuh"
@@ -32,7 +33,10 @@ struct FftFirArgs {
     int V;              // valid outputs per block
 };
 
-__global__ void __launch_bounds__(kFfThreads) fir_fft_kernel(const FftFirArgs a) {
+// MINB = CTAs per SM the register allocation must allow: the unconstrained build took 171 registers = ONE 256-thread
+// CTA per SM (ncu: 12 % of the warp slots active); 128 registers (no spills) give two, 80 (288 B of spills) three.
+template <int MINB>
+__global__ void __launch_bounds__(kFfThreads, MINB) fir_fft_kernel(const FftFirArgs a) {
     constexpr int N = kNF, T = kFfThreads;
     extern __shared__ __align__(16) unsigned char ffsm[];
     float2 *sm = reinterpret_cast<float2 *>(ffsm);
@@ -123,7 +127,10 @@ int32_t fir_fft_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, s
     a.V = kNF - (int)(f->ntaps - 1);
     const unsigned grid = (unsigned)ceil_div(n_out, (size_t)a.V);
     const size_t smem = (size_t)(kNF + kNF / 16) * sizeof(float2);
-    fir_fft_kernel<<<grid, kFfThreads, smem, stream>>>(a);
+    static const int minb = [] { const char *e = getenv("B2S_FFTFIR_MINB"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 3 ? v : 2; }();
+    if (minb == 1) fir_fft_kernel<1><<<grid, kFfThreads, smem, stream>>>(a);
+    else if (minb == 3) fir_fft_kernel<3><<<grid, kFfThreads, smem, stream>>>(a);
+    else fir_fft_kernel<2><<<grid, kFfThreads, smem, stream>>>(a);
     B2S_CHECK_LAUNCH(ctx);
     return B2S_OK;
 }

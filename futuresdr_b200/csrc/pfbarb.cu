@@ -157,8 +157,11 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
     const long long o_end = sb1 == P.nsub ? P.nout : pfb_sub_start(P, sb1).o_start;
     const long long s_lo = max(first.s_beg, 0ll);                // first sample of the CTA (call coordinates)
     const long long s_hi = pfb_sub_start(P, sb1 - 1).s_end;
+    // arms in shared memory with an ODD row stride: the threads of a warp read different arms at the same tap index,
+    // and with stride T = 16 floats all 32 of them hit two banks (ncu: 176 M bank conflicts, 16 % issue utilisation)
+    const int TS = P.arms_in_smem ? (T | 1) : T;
     if (P.arms_in_smem)
-        for (int j = threadIdx.x; j < N * T; j += kPaThreads) s_arms[j] = P.arms[j];
+        for (int j = threadIdx.x; j < N * T; j += kPaThreads) s_arms[(j / T) * TS + (j % T)] = P.arms[j];
     if (P.tile_in_smem) {
         // outputs of sample s read [hist | in][s .. s+T] (Boundary reaches one item further back)
         const int cnt = (int)(s_hi - s_lo) + T + 1;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
         const int s0 = boundary ? s1 - 1 : s1;
         const uint32_t b0 = d_b0[o], b1 = boundary ? 0u : b0 + 1u;
         const float mu = d_mu[o];
-        const float *a0 = A + (size_t)b0 * T, *a1 = A + (size_t)b1 * T;
+        const float *a0 = A + (size_t)b0 * TS, *a1 = A + (size_t)b1 * TS;
         float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
         if (P.tile_in_smem) {
             const float2 *xa = s_x + s0, *xb = s_x + s1;
@@ -478,9 +481,10 @@ int32_t b2s_pfbarb_exec(b2s_pfbarb *p, const void *d_in, size_t n_in, void *d_ou
     const size_t tile_items = sub_per_cta * P.sb_len + p->T + 2;
     P.tile_in_smem = tile_items * sizeof(float2) <= 64 * 1024;
     P.tile_cap = (int)tile_items;
-    P.arms_in_smem = arms_bytes <= 64 * 1024;
+    const size_t arms_smem_bytes = p->num_filters * (p->T | 1) * sizeof(float);        // odd row stride (bank conflicts)
+    P.arms_in_smem = arms_smem_bytes <= 64 * 1024;
     const size_t smem = 3 * kDescCap * sizeof(uint32_t) + (P.tile_in_smem ? tile_items * sizeof(float2) : 0) +
-                        (P.arms_in_smem ? arms_bytes : 0);
+                        (P.arms_in_smem ? arms_smem_bytes : 0);
     pfb_kernel<<<grid, kPaThreads, smem, ctx->stream>>>(P);
     B2S_CHECK_LAUNCH(ctx);
     pfb_hist_update<<<1, 256, T * sizeof(float2), ctx->stream>>>(p->d_hist, in, T, (long long)n);

@@ -54,8 +54,21 @@ struct SpArgs {
     float a, d;
 };
 
+__device__ __forceinline__ void sp_cp_async8(void *dst_smem, const void *src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sp_cp_async16(void *dst_smem, const void *src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+
+// The next frame of a group is fetched with cp.async into a raw staging row while the current one is being
+// transformed: the first FFT pass reads the staging row, and from the barrier that ends it the row is free again, so
+// the fetch of frame c+1 overlaps passes 2.. and the averaging of frame c.  (The first version read the frame with
+// plain loads at the top of every round: 2 CTAs per SM x serialized load / compute phases = 40 % of HBM.)
 template <int LOG2N>
-__global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpArgs p) {
+__global__ void __launch_bounds__(kSpThreads, (LOG2N <= 12 ? 3 : 1)) spectrum_kernel(const SpArgs p) {
     constexpr int N = 1 << LOG2N;
     constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > kSpThreads) ? kSpThreads : N / 16);   // threads per transform
     constexpr int FPB = kSpThreads / T;
@@ -65,19 +78,28 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpArgs p) {
     const int t = threadIdx.x % T, fl = threadIdx.x / T;
     const int g = blockIdx.x * FPB + fl;
     const bool live = g < p.groups;
-    float2 *sm = reinterpret_cast<float2 *>(ssm) + (size_t)fl * NP;
+    float2 *sm = reinterpret_cast<float2 *>(ssm) + (size_t)fl * NP;           // padded FFT buffer of this group
+    float2 *raw = reinterpret_cast<float2 *>(ssm) + (size_t)FPB * NP + (size_t)fl * N;   // staging row (next frame)
     float *sP = reinterpret_cast<float *>(sm);              // |X|^2 of the current frame (aliases the FFT buffer)
     const long long f0 = (long long)(live ? g : p.groups - 1) * p.C;
     const long long nf = live ? min(p.C, p.nframes - f0) : 0;
     float avg[NB];
 #pragma unroll
     for (int k = 0; k < NB; k++) avg[k] = 0.0f;
+    auto fetch = [&](long long c) {                          // frame c of this group -> raw (idle rounds re-fetch frame 0)
+        const float4 *src = reinterpret_cast<const float4 *>(p.in + (f0 + (c < nf ? c : 0)) * N);
+        for (int i = t; i < N / 2; i += T) sp_cp_async16(reinterpret_cast<float4 *>(raw) + i, src + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0);
     for (long long c = 0; c < p.C; c++) {                   // every group of the CTA runs C rounds (barriers inside)
         const bool act = c < nf;
-        const float2 *gin = p.in + (f0 + (act ? c : 0)) * N;
-        fft_passes<LOG2N, T>([&](int idx) { return __ldg(gin + idx); },
-                             [&](int idx, float2 v) { sP[idx] = fmaf(v.x, v.x, v.y * v.y); },   // norm_sqr
-                             sm, p.tw, t, false);        // (the barrier that frees `sm` is the one closing the loop body)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                     // raw holds frame c; everyone is done with sP of frame c-1
+        fft_passes_hook<LOG2N, T>([&](int idx) { return raw[idx]; },
+                                  [&]() { if (c + 1 < p.C) fetch(c + 1); },
+                                  [&](int idx, float2 v) { sP[idx] = fmaf(v.x, v.x, v.y * v.y); },   // norm_sqr
+                                  sm, p.tw, t);
         if (act) {
             const long long fs = f0 + c;                     // frame index within the call
             const bool emit = ((p.i0 + fs + 1) % p.history) == 0;
@@ -91,8 +113,6 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpArgs p) {
                 if (emit) orow[p.shift ? ((b + N / 2) & (N - 1)) : b] = avg[k];
             }
         }
-        // the next round's first pass stores into `sm` before its own barrier: everyone must be done with sP
-        __syncthreads();
     }
     if (live) {
 #pragma unroll
@@ -160,7 +180,7 @@ int32_t launch_spectrum(b2s_spectrum *p, const SpArgs &a, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
     constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > kSpThreads) ? kSpThreads : N / 16);
     constexpr int FPB = kSpThreads / T;
-    constexpr size_t smem = (size_t)FPB * (N + N / 16) * sizeof(float2);
+    constexpr size_t smem = (size_t)FPB * (N + N / 16 + N) * sizeof(float2);
     auto kern = spectrum_kernel<LOG2N>;
     if (smem > 48 * 1024) B2S_CUDA(p->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)ceil_div((size_t)a.groups, (size_t)FPB);
@@ -172,7 +192,7 @@ int32_t launch_spectrum(b2s_spectrum *p, const SpArgs &a, cudaStream_t stream) {
 template <int LOG2N> int spectrum_resident() {         // CTAs of this instantiation that fit one SM
     constexpr int N = 1 << LOG2N;
     constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > kSpThreads) ? kSpThreads : N / 16);
-    constexpr size_t smem = (size_t)(kSpThreads / T) * (N + N / 16) * sizeof(float2);
+    constexpr size_t smem = (size_t)(kSpThreads / T) * (N + N / 16 + N) * sizeof(float2);
     auto kern = spectrum_kernel<LOG2N>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 1;
@@ -251,6 +271,7 @@ int32_t b2s_spectrum_exec(b2s_spectrum *p, const void *d_in, size_t n_in, void *
     *consumed = frames * N; *produced = rows * N;
     if (frames == 0) return B2S_OK;
     if (!d_in || (rows && !d_out)) return b2s_fail(ctx, B2S_EINVAL, "b2s_spectrum_exec: NULL buffer");
+    if (reinterpret_cast<uintptr_t>(d_in) & 15) return b2s_fail(ctx, B2S_EINVAL, "b2s_spectrum_exec: the input slice must be 16-byte aligned");
     DeviceGuard g(ctx->device);
     NvtxRange nvtx("b2s_spectrum_exec");
     cudaStream_t st = ctx->stream;

@@ -93,6 +93,8 @@ class _FilterBase:
         op, n_out, odev, _k2 = _buf(output, self.sample_dtype, writable=True)
         if idev != odev:
             raise ValueError("input and output must both be device slices or both host slices")
+        if idev and (input.device.index != self.ctx.device or output.device.index != self.ctx.device):
+            raise ValueError(f"device slices must live on the filter's context device cuda:{self.ctx.device}")
         c, p, st = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
         fn = type(self)._exec if idev else type(self)._host
         if fn is None:

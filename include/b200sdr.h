@@ -67,7 +67,8 @@ typedef enum {
                           * vectors on DIRECT).  Non-finite input: a NaN/Inf sample at index i makes every output of
                           * the 128-sample blocks whose K-range contains it non-finite (inside [i-K, i+131],
                           * K = 128*ceil((ntaps+127)/128), a superset of the reference's [i-ntaps+1, i]); all other
-                          * outputs are unaffected and no finite output is ever wrong.  Streams that may carry
+                          * outputs are unaffected and no finite output is ever wrong.  f32 DENORMAL samples count as
+                          * zero (tensor-core operands are flush-to-zero).  Streams that may carry
                           * non-finite samples and need the reference's exact propagation: use B2S_ALGO_DIRECT. */
     B2S_ALGO_FFT    = 3  /* overlap-save FFT convolution (c32 samples, 64..2049 taps, decim == 1)  */
 } b2s_algo;

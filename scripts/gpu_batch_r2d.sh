@@ -1,6 +1,6 @@
 # round-2 batch D (1 GPU): whole GPU suite, full bench line with the secondary configs, per-kernel numbers, ncu captures
 mkdir -p gpurun_out
-echo "--- suite"; timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -25
+echo "--- suite"; timeout 2400 python -m pytest tests -m gpu -q -x 2>&1 | tail -25
 echo "--- smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 echo "--- bench"; timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2d_n1.json 2> gpurun_out/bench_r2d_n1.err; tail -3 gpurun_out/bench_r2d_n1.err; python - <<'PY'
 import json
@@ -22,3 +22,6 @@ $NCU -k regex:apply_kernel -s 1 -c 1 -o gpurun_out/prof_r2_demod python scripts/
 $NCU -k regex:fir_tc_kernel -s 3 -c 1 -o gpurun_out/prof_r2_tc python bench.py --steps 3 --warmup 3 --no-cpu --no-secondary --no-sustained > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-secondary --no-sustained > /dev/null 2>&1
 ls -la gpurun_out | tail -14
+echo "--- overlap-save occupancy A/B"; for mb in 1 2 3; do B2S_FFTFIR_MINB=$mb python scripts/bench_configs.py --only fir1024 2>&1 | tail -1 | cut -c1-150; done
+echo "--- fft sizes"; python scripts/bench_configs.py --only fft 2>&1 | tail -8 | cut -c1-150
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r2_fused.csv python scripts/bench_configs.py --only fused > /dev/null 2>&1; grep -E "spectrum|chan_fused" gpurun_out/launches_r2_fused.csv | awk -F'","' '{print $5, $NF}' | sort | uniq -c | sort -rn | head -12

@@ -1,7 +1,10 @@
 #!/bin/bash
-# gpurun_retry.sh LOGFILE [gpurun args...]: retries while the pod answers "transient" (nothing charged)
+# gpurun_retry.sh LOGFILE [gpurun args...]: retries while the pod answers "transient" (nothing charged) or while an
+# earlier call of this repo is still in flight ("refused")
 LOG=$1; shift
-for attempt in 1 2 3 4 5 6 7 8 9 10 11 12; do
+for attempt in $(seq 1 40); do
   /usr/local/graft/bin/gpurun "$@" > "$LOG" 2>&1
-  if grep -q "status=transient" "$LOG"; then sleep 90; else break; fi
+  if grep -q "status=transient" "$LOG"; then sleep 90;
+  elif grep -q "status=refused" "$LOG"; then sleep 45;
+  else break; fi
 done

@@ -95,9 +95,10 @@ def test_boxcar_on_dc_documented_worst_case():
     print(f"[tensor-structured] boxcar-on-DC worst e_f64 {worst:.2e} (bound 3.1e-5)")
 
 
-def test_denormal_samples_flush_consistently():
-    """Samples in the f32 denormal range: the bf16 split flushes nothing (bf16 has the f32 exponent range), the
-    products underflow in f32 exactly like the reference's.  Absolute check (the scale would underflow)."""
+def test_denormal_samples_are_flushed_to_zero():
+    """Contract (include/b200sdr.h): the tensor path treats f32 DENORMAL samples as zero (the bf16 operands of
+    tcgen05.mma are flush-to-zero), where the reference's scalar loop keeps them.  The difference is bounded by
+    ||taps||_1 * 1.18e-38 (the largest denormal) -- 280 dB below full scale -- and normal samples are unaffected."""
     rng = np.random.default_rng(7)
     n = 20000
     taps = rng.uniform(-1, 1, 128).astype(np.float32)
@@ -105,7 +106,13 @@ def test_denormal_samples_flush_consistently():
     y, p = _run(taps, x)
     _, _, _, ref = orc.fir(taps, x, n)
     assert np.all(np.isfinite(y.view(np.float32)))
-    assert float(np.max(np.abs(y - ref))) <= 1e-5 * float(np.sum(np.abs(taps))) * 1e-41 * 6 + 1e-44
+    assert float(np.max(np.abs(y - ref))) <= float(np.sum(np.abs(taps))) * 1.18e-38
+    # a stream that mixes normal samples with denormal ones: the normal part is filtered as usual
+    x2 = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    x2[::3] *= np.float32(1e-41)
+    y2, _ = _run(taps, x2)
+    _, _, _, ref2 = orc.fir(taps, x2, n)
+    assert float(np.max(np.abs(y2 - ref2))) <= 1e-5 * float(np.sum(np.abs(taps))) * float(np.max(np.abs(x2)))
 
 
 @pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan])
