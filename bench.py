@@ -387,6 +387,39 @@ def sec_config1_perf_fir(torch, fb, dev, args):
             got.append(m)
     sec = _time_passes(torch, gpu_pass, reps=10, warm=2)
     assert all(m == n - stages * (ntaps - 1) for m in got)
+    # the same 30 launches captured ONCE in a CUDA graph and replayed (launch-bound inner loops belong in graphs):
+    # a context on a dedicated stream, the plan created before capture, the pass captured on that stream
+    graph_sec = None
+    try:
+        gs = torch.cuda.Stream(dev)
+        with torch.cuda.stream(gs):
+            gctx = fb.Context(dev.index, stream=gs.cuda_stream)
+            gfir = fb.FirFilter(taps, sample_dtype=np.float32, ctx=gctx)
+
+            def graph_body():
+                for _p in range(pipes):
+                    cur, m = xd, n
+                    for s_ in range(stages):
+                        c, p, st = gfir.filter(cur[:m], bufs[s_ & 1])
+                        cur, m = bufs[s_ & 1], p
+            graph_body()
+            gs.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=gs):
+                graph_body()
+            for _ in range(3):
+                g.replay()
+            gs.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(gs)
+            for _ in range(20):
+                g.replay()
+            e1.record(gs)
+            gs.synchronize()
+            graph_sec = e0.elapsed_time(e1) * 1e-3 / 20
+    except Exception as e:  # noqa: BLE001
+        graph_sec = None
+        graph_err = repr(e)[:200]
     # end to end: host vector in, host vector out per pipe (VectorSource / VectorSink roles)
     h_in = torch.from_numpy(x).pin_memory()
     h_out = torch.empty(n, dtype=torch.float32).pin_memory()
@@ -412,7 +445,10 @@ def sec_config1_perf_fir(torch, fb, dev, args):
                    "pipes": pipes, "stages": stages, "samples": n, "ntaps": ntaps, "algo": {1: "direct", 2: "tensor", 3: "fft"}.get(fir.algo)},
         "metric": "Msamples/s", "value": val, "unit": "Msamples/s (pipes x samples / elapsed, as perf/fir prints elapsed)",
         "ms_per_pass": sec * 1e3, "gpu_launches_per_pass": pipes * stages,
-        "roofline": _roofline(8.0 * n * stages * pipes, sec, "8 B/sample/stage; 30 launches of ~4 MB each: launch-latency bound"),
+        "cuda_graph": ({"value": pipes * n / graph_sec / 1e6, "unit": "Msamples/s", "ms_per_pass": graph_sec * 1e3,
+                        "note": "the same pipes x stages launches captured once in a CUDA graph and replayed"}
+                       if graph_sec else {"error": locals().get("graph_err")}),
+        "roofline": _roofline(8.0 * n * stages * pipes, min(sec, graph_sec or sec), "8 B/sample/stage; 30 launches of ~4 MB each: launch-latency bound (best of eager / graph replay)"),
         "cpu_baseline": {"value": pipes * n / cpu_s / 1e6, "unit": "Msamples/s", "cores": pipes, "kind": "port",
                          "sample": "the whole config: 5 pipes x 6 stages x 1 M samples, oracle port of fir.rs:52-91 (strict order), one thread per pipe"},
         "e2e": {"value": pipes * n / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * n * pipes,
