@@ -110,7 +110,8 @@ constexpr int kFftThreads = 256;
 // 171 registers = one 256-thread CTA per SM although shared memory admits three -> cap at 128 (16 B of spills), two
 // CTAs.  16384: one transform fills 139 KiB of shared memory, so one CTA per SM whatever we do -- 512 threads halve
 // the butterflies (and registers) per thread and double the warps that hide latency.
-template <int LOG2N> struct FftCfg { static constexpr int THREADS = LOG2N >= 14 ? 512 : 256, MINB = LOG2N == 13 ? 2 : 1; };
+// (<= 4096: three CTAs per SM as before -- naming a minimum of 1 let ptxas take 111 registers and cost 15 % at 4096.)
+template <int LOG2N> struct FftCfg { static constexpr int THREADS = LOG2N >= 14 ? 512 : 256, MINB = LOG2N >= 14 ? 1 : (LOG2N == 13 ? 2 : 3); };
 
 template <int LOG2N>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) fft_kernel(const FftArgs a) {

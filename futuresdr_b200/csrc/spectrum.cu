@@ -123,55 +123,64 @@ __global__ void __launch_bounds__(kSpThreads, (LOG2N <= 12 ? 3 : 1)) spectrum_ke
     }
 }
 
-// carry scan across groups: one warp per bin.  fin[g][bin] (local final of group g) is overwritten by the state
-// the group STARTS from; avg[bin] (in: state before the call) receives the state after the call.
-__global__ void __launch_bounds__(256) spectrum_scan(float *fin, float *avg, int n, int groups, float A, float A_last) {
-    const int bin = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (bin >= n) return;
-    const int per = (groups + 31) / 32;
-    const int g0 = lane * per, g1 = min(g0 + per, groups);
-    // compose this lane's groups: x -> L + M*x
+// Carry scan across the groups + fix-up of the emitted rows, one kernel.  A CTA owns 32 adjacent bins (the lanes of
+// a warp: every load / store below is one coalesced 128-byte line) and cuts the groups into 32 segments, one per warp:
+//   1. each warp composes the affine maps  x -> final_g + A_g * x  of its segment (sequential over ~groups/32 groups);
+//   2. the 32 composites of a bin are scanned through shared memory (sequential over segments, 32 lanes = 32 bins);
+//   3. each warp walks its segment again with the now known incoming state: it records nothing but FIXES the rows its
+//      groups emitted,  out[row][bin] += a^k * carry_g[bin]  (+ the optional k*log10), and the last warp leaves the
+//      state after the call in avg[].
+// (The first version gave a warp to each bin with the lanes striding over groups: 4-byte loads 8 KiB apart, 207 us for
+// 7 MB of carries -- as long as the FFT kernel itself -- plus an 88 us element-wise fix-up kernel with a 64-bit
+// division per element.)
+constexpr int kScanSegs = 32;
+__global__ void __launch_bounds__(32 * kScanSegs)
+spectrum_scan_fixup(const float *__restrict__ fin, float *avg, float *out, const float *__restrict__ apow, int n, int groups,
+                    long long C, long long nframes, int history, int i0, float A, float A_last, float log10_k) {
+    __shared__ float sL[kScanSegs][33], sM[kScanSegs][33], sX[kScanSegs][33];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int bin = blockIdx.x * 32 + lane;
+    const bool live = bin < n;
+    const int per = (groups + kScanSegs - 1) / kScanSegs;
+    const int g0 = min(seg * per, groups), g1 = min(g0 + per, groups);
+    // 1. compose this segment
     float L = 0.0f, M = 1.0f;
+    if (live) {
+#pragma unroll 4
+        for (int g = g0; g < g1; g++) {
+            const float Ag = (g == groups - 1) ? A_last : A;
+            L = fmaf(Ag, L, __ldg(fin + (size_t)g * n + bin));
+            M *= Ag;
+        }
+    }
+    sL[seg][lane] = L; sM[seg][lane] = M;
+    __syncthreads();
+    // 2. warp 0: state entering every segment of its 32 bins
+    if (seg == 0) {
+        float x = live ? avg[bin] : 0.0f;
+        for (int sgm = 0; sgm < kScanSegs; sgm++) {
+            sX[sgm][lane] = x;
+            x = fmaf(sM[sgm][lane], x, sL[sgm][lane]);
+        }
+        if (live) avg[bin] = x;                              // state after the call
+    }
+    __syncthreads();
+    // 3. walk the segment again: fix the rows each group emitted
+    if (!live) return;
+    float x = sX[seg][lane];
     for (int g = g0; g < g1; g++) {
         const float Ag = (g == groups - 1) ? A_last : A;
-        L = fmaf(Ag, L, fin[(size_t)g * n + bin]);
-        M *= Ag;
-    }
-    // inclusive shuffle scan of the affine maps over the lanes
-    float SL = L, SM = M;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const float pl = __shfl_up_sync(0xffffffffu, SL, off), pm = __shfl_up_sync(0xffffffffu, SM, off);
-        if (lane >= off) { SL = fmaf(SM, pl, SL); SM *= pm; }
-    }
-    const float x0 = avg[bin];
-    // state entering this lane's first group = (composition of all previous lanes)(x0)
-    float el = __shfl_up_sync(0xffffffffu, SL, 1), em = __shfl_up_sync(0xffffffffu, SM, 1);
-    float x = lane == 0 ? x0 : fmaf(em, x0, el);
-    for (int g = g0; g < g1; g++) {
-        const float Ag = (g == groups - 1) ? A_last : A;
-        const float f = fin[(size_t)g * n + bin];
-        fin[(size_t)g * n + bin] = x;                        // carry INTO group g
-        x = fmaf(Ag, x, f);
-    }
-    const float xe = __shfl_sync(0xffffffffu, x, min(31, (groups - 1) / per));   // the lane that owns the last group
-    if (lane == 0) avg[bin] = xe;
-}
-
-__global__ void __launch_bounds__(256)
-spectrum_fixup(float *out, const float *__restrict__ carry, const float *__restrict__ apow, int n, long long n_emit,
-               long long C, int history, int i0, float log10_k) {
-    const long long total = n_emit * n;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const long long o = e / n;
-        const int bin = (int)(e - o * n);
-        const long long f = (o + 1) * history - i0 - 1;       // frame (within the call) that emitted row o
-        const long long g = f / C;
-        const int k = (int)(f - g * C) + 1;
-        float v = fmaf(apow[k], carry[(size_t)g * n + bin], out[e]);
-        if (log10_k != 0.0f) v = log10_k * log10f(v);
-        out[e] = v;
+        const long long fb = (long long)g * C, fe = min(fb + C, nframes);
+        // first frame of the group that emits: (i0 + f + 1) % history == 0
+        long long f = fb + ((history - (int)((i0 + fb + 1) % history)) % history);
+        for (; f < fe; f += history) {
+            const long long row = (i0 + f + 1) / history - 1;
+            float *o = out + row * n + bin;
+            float v = fmaf(apow[f - fb + 1], x, *o);
+            if (log10_k != 0.0f) v = log10_k * log10f(v);
+            *o = v;
+        }
+        x = fmaf(Ag, x, __ldg(fin + (size_t)g * n + bin));
     }
 }
 
@@ -334,16 +343,10 @@ int32_t b2s_spectrum_exec(b2s_spectrum *p, const void *d_in, size_t n_in, void *
     if (rc != B2S_OK) return rc == B2S_EUNSUPPORTED ? b2s_fail(ctx, rc, "b2s_spectrum_exec: unsupported size") : rc;
     const double ad = (double)(1.0f - p->decay);
     const size_t c_last = frames - (groups - 1) * C;
-    spectrum_scan<<<(unsigned)ceil_div(N, (size_t)8), 256, 0, st>>>(p->d_final, p->d_avg, (int)N, (int)groups,
-                                                                      (float)std::pow(ad, (double)C), (float)std::pow(ad, (double)c_last));
+    spectrum_scan_fixup<<<(unsigned)ceil_div(N, (size_t)32), 32 * kScanSegs, 0, st>>>(
+        p->d_final, p->d_avg, (float *)d_out, p->d_pow, (int)N, (int)groups, (long long)C, (long long)frames, (int)h,
+        (int)p->i, (float)std::pow(ad, (double)C), (float)std::pow(ad, (double)c_last), p->log10_k);
     B2S_CHECK_LAUNCH(ctx);
-    if (rows) {
-        const size_t total = rows * N;
-        const unsigned grid = (unsigned)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)ctx->sm_count * 8);
-        spectrum_fixup<<<grid, 256, 0, st>>>((float *)d_out, p->d_final, p->d_pow, (int)N, (long long)rows, (long long)C,
-                                              (int)h, (int)p->i, p->log10_k);
-        B2S_CHECK_LAUNCH(ctx);
-    }
     p->i = (p->i + frames) % h;
     return B2S_OK;
 }
