@@ -217,9 +217,12 @@ class Fft(Block):
             io.finished = True
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_fft_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_fft_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class ApplyOp(enum.IntEnum):
@@ -275,9 +278,12 @@ class Apply(Block):
             io.finished = True
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_apply_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_apply_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class PfbArbResampler(Block):
@@ -314,9 +320,12 @@ class PfbArbResampler(Block):
         check(lib.b2s_pfbarb_reset(self._h), self.ctx.handle)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_pfbarb_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_pfbarb_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class Rotator:
@@ -343,9 +352,12 @@ class Rotator:
         check(lib.b2s_rotator_reset(self._h), self.ctx.handle)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_rotator_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_rotator_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class XlatingFir(Block):
@@ -416,9 +428,12 @@ class PfbSynthesizer(Block):
             io.finished = True
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_synth_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_synth_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class MovingAvg(Block):
@@ -448,9 +463,12 @@ class MovingAvg(Block):
         self.output.produce(p.value)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_mavg_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_mavg_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class SpectrumPipe(Block):
@@ -493,9 +511,12 @@ class SpectrumPipe(Block):
         check(lib.b2s_spectrum_reset(self._h), self.ctx.handle)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_spectrum_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_spectrum_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class PfbChannelizer(Block):
@@ -540,9 +561,12 @@ class PfbChannelizer(Block):
             io.finished = True
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.b2s_chan_destroy(self._h)
-            self._h = None
+        try:                                   # (module globals may already be gone at interpreter shutdown)
+            if getattr(self, "_h", None):
+                lib.b2s_chan_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class Mocker:

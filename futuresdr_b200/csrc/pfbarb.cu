@@ -46,7 +46,8 @@ struct b2s_pfbarb {
     b2s_ctx *ctx = nullptr;
     size_t num_filters = 0, T = 0, ntaps = 0;
     float rate = 1.f, delay = 1.f;
-    float *d_arms = nullptr;       // [num_filters][T], time-reversed: arm_b[T-1-j]
+    float2 *d_arms = nullptr;      // [num_filters][T] PAIRS (arm_b[T-1-j], arm_{(b+1) % N}[T-1-j]), time-reversed: an output blends
+                                   // arm b and its successor (arm 0 after the last one: the Boundary state), one 8-byte load per tap
     float2 *d_circ = nullptr;      // 2*T, the reference's circular buffer (only used while filling)
     float2 *d_hist = nullptr;      // T samples of history once filled
     // WindowBuffer bookkeeping (host)
@@ -105,7 +106,7 @@ __device__ __forceinline__ float2 pfb_x(const float2 *__restrict__ hist, const f
 struct PaParams {
     const float2 *in, *hist;
     float2 *out;
-    const float *arms;
+    const float2 *arms;            // [N][T] pairs (arm b, arm b+1)
     const SubRec *recs;            // periodic: the plan's table; otherwise this call's records
     long long n_in, nsub, nout;
     int sub_per_cta, N, T, sb_len;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
     uint32_t *d_b0 = d_s1 + kDescCap;                            // arm of y0
     float *d_mu = reinterpret_cast<float *>(d_b0 + kDescCap);
     float2 *s_x = reinterpret_cast<float2 *>(d_mu + kDescCap);   // the CTA's span of [hist | in]
-    float *s_arms = reinterpret_cast<float *>(s_x + (P.tile_in_smem ? P.tile_cap : 0));
+    float2 *s_arms = s_x + (P.tile_in_smem ? P.tile_cap : 0);
     const int N = P.N, T = P.T;
 
     const long long sb0 = (long long)blockIdx.x * P.sub_per_cta;
@@ -157,14 +158,15 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
     const long long o_end = sb1 == P.nsub ? P.nout : pfb_sub_start(P, sb1).o_start;
     const long long s_lo = max(first.s_beg, 0ll);                // first sample of the CTA (call coordinates)
     const long long s_hi = pfb_sub_start(P, sb1 - 1).s_end;
-    // arms in shared memory with an ODD row stride: the threads of a warp read different arms at the same tap index,
-    // and with stride T = 16 floats all 32 of them hit two banks (ncu: 176 M bank conflicts, 16 % issue utilisation)
+    // arm pairs in shared memory with an ODD row stride: the threads of a warp read different arms at the same tap
+    // index, and with a stride of 16 all 32 of them hit two banks (ncu: 176 M bank conflicts, 16 % issue utilisation)
     const int TS = P.arms_in_smem ? (T | 1) : T;
     if (P.arms_in_smem)
         for (int j = threadIdx.x; j < N * T; j += kPaThreads) s_arms[(j / T) * TS + (j % T)] = P.arms[j];
     if (P.tile_in_smem) {
-        // outputs of sample s read [hist | in][s .. s+T] (Boundary reaches one item further back)
-        const int cnt = (int)(s_hi - s_lo) + T + 1;
+        // the outputs of sample s read [hist | in][s+1 .. s+T] (Boundary: [s .. s+T-1] as well), s in [s_lo, s_hi):
+        // items s_lo .. s_hi+T-1.  (One more would read in[n_in]: compute-sanitizer caught exactly that.)
+        const int cnt = (int)(s_hi - s_lo) + T;
         for (int j = threadIdx.x; j < cnt; j += kPaThreads) s_x[j] = pfb_x(P.hist, P.in, T, s_lo + j);
     }
 
@@ -204,33 +206,42 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
     }
     __syncthreads();
 
-    // ---- phase 2: evaluate the outputs
-    const float *A = P.arms_in_smem ? s_arms : P.arms;
+    // ---- phase 2: evaluate the outputs.  y0 = arm b0, y1 = arm b0+1 on the same window (Interpolate), or arm N-1 on the
+    // previous window and arm 0 on the current one (Boundary): per tap ONE 8-byte sample load and ONE 8-byte tap-pair load
+    const float2 *A = P.arms_in_smem ? s_arms : P.arms;
     const uint32_t cnt = (uint32_t)(o_end - o_first);
     for (uint32_t o = threadIdx.x; o < cnt; o += kPaThreads) {
         const uint32_t w = d_s1[o];
         const bool boundary = (w >> 31) != 0;
         const int s1 = (int)(w & 0x7fffffffu);                   // relative to s_lo
-        const int s0 = boundary ? s1 - 1 : s1;
-        const uint32_t b0 = d_b0[o], b1 = boundary ? 0u : b0 + 1u;
+        const uint32_t b0 = d_b0[o];
         const float mu = d_mu[o];
-        const float *a0 = A + (size_t)b0 * TS, *a1 = A + (size_t)b1 * TS;
+        const float2 *pr = A + (size_t)b0 * TS;
         float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
         if (P.tile_in_smem) {
-            const float2 *xa = s_x + s0, *xb = s_x + s1;
+            const float2 *xb = s_x + s1;
+            if (!boundary) {
 #pragma unroll 4
-            for (int j = 0; j < T; j++) {
-                const float2 va = xa[j], vb = xb[j];
-                const float t0 = a0[j], t1 = a1[j];
-                y0.x = fmaf(va.x, t0, y0.x); y0.y = fmaf(va.y, t0, y0.y);
-                y1.x = fmaf(vb.x, t1, y1.x); y1.y = fmaf(vb.y, t1, y1.y);
+                for (int j = 0; j < T; j++) {
+                    const float2 v = xb[j], t = pr[j];
+                    y0.x = fmaf(v.x, t.x, y0.x); y0.y = fmaf(v.y, t.x, y0.y);
+                    y1.x = fmaf(v.x, t.y, y1.x); y1.y = fmaf(v.y, t.y, y1.y);
+                }
+            } else {
+                const float2 *xa = xb - 1;
+                for (int j = 0; j < T; j++) {
+                    const float2 va = xa[j], vb = xb[j], t = pr[j];
+                    y0.x = fmaf(va.x, t.x, y0.x); y0.y = fmaf(va.y, t.x, y0.y);
+                    y1.x = fmaf(vb.x, t.y, y1.x); y1.y = fmaf(vb.y, t.y, y1.y);
+                }
             }
         } else {
+            const int s0 = boundary ? s1 - 1 : s1;
             for (int j = 0; j < T; j++) {
                 const float2 va = pfb_x(P.hist, P.in, T, s_lo + s0 + j), vb = pfb_x(P.hist, P.in, T, s_lo + s1 + j);
-                const float t0 = a0[j], t1 = a1[j];
-                y0.x = fmaf(va.x, t0, y0.x); y0.y = fmaf(va.y, t0, y0.y);
-                y1.x = fmaf(vb.x, t1, y1.x); y1.y = fmaf(vb.y, t1, y1.y);
+                const float2 t = pr[j];
+                y0.x = fmaf(va.x, t.x, y0.x); y0.y = fmaf(va.y, t.x, y0.y);
+                y1.x = fmaf(vb.x, t.y, y1.x); y1.y = fmaf(vb.y, t.y, y1.y);
             }
         }
         // (1.0 - mu) * buff[0] + mu * buff[1]   (arb_resampler.rs:153,:176)
@@ -347,11 +358,14 @@ int32_t b2s_pfbarb_plan_c32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_
         size_t j = 0;
         for (size_t idx = i; idx < ntaps; idx += num_filters, j++) arms[i * T + (T - 1 - j)] = taps[idx];   // reversed
     }
-    cudaError_t e1 = cudaMalloc((void **)&p->d_arms, arms.size() * sizeof(float));
+    std::vector<float2> pairs(num_filters * T);
+    for (size_t b = 0; b < num_filters; b++)
+        for (size_t j = 0; j < T; j++) pairs[b * T + j] = make_float2(arms[b * T + j], arms[((b + 1) % num_filters) * T + j]);
+    cudaError_t e1 = cudaMalloc((void **)&p->d_arms, pairs.size() * sizeof(float2));
     cudaError_t e2 = cudaMalloc((void **)&p->d_circ, 2 * T * sizeof(float2));
     cudaError_t e3 = cudaMalloc((void **)&p->d_hist, T * sizeof(float2));
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { b2s_pfbarb_destroy(p); return b2s_fail(ctx, B2S_ENOMEM, "pfbarb buffers"); }
-    B2S_CUDA(ctx, cudaMemcpyAsync(p->d_arms, arms.data(), arms.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    B2S_CUDA(ctx, cudaMemcpyAsync(p->d_arms, pairs.data(), pairs.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     p->periodic = getenv("B2S_PFBARB_NO_PERIODIC") ? false : build_periodic_schedule(p);
     if (p->periodic) {
         if (cudaMalloc((void **)&p->d_tab, p->tab.size() * sizeof(SubRec)) != cudaSuccess) {
@@ -477,11 +491,10 @@ int32_t b2s_pfbarb_exec(b2s_pfbarb *p, const void *d_in, size_t n_in, void *d_ou
     sub_per_cta = std::min<size_t>(sub_per_cta, kPaThreads);
     P.sub_per_cta = (int)sub_per_cta;
     const unsigned grid = (unsigned)ceil_div((size_t)P.nsub, sub_per_cta);
-    const size_t arms_bytes = p->num_filters * p->T * sizeof(float);
     const size_t tile_items = sub_per_cta * P.sb_len + p->T + 2;
     P.tile_in_smem = tile_items * sizeof(float2) <= 64 * 1024;
     P.tile_cap = (int)tile_items;
-    const size_t arms_smem_bytes = p->num_filters * (p->T | 1) * sizeof(float);        // odd row stride (bank conflicts)
+    const size_t arms_smem_bytes = p->num_filters * (p->T | 1) * sizeof(float2);       // odd row stride (bank conflicts)
     P.arms_in_smem = arms_smem_bytes <= 64 * 1024;
     const size_t smem = 3 * kDescCap * sizeof(uint32_t) + (P.tile_in_smem ? tile_items * sizeof(float2) : 0) +
                         (P.arms_in_smem ? arms_smem_bytes : 0);

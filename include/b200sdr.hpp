@@ -392,6 +392,30 @@ private:
     const Instance &inst_; size_t width_; b2s_mavg *h_ = nullptr;
 };
 
+// The spectrum flowgraph's compute chain as one block: Fft::with_options(n, Forward, fft_shift, None) ->
+// Apply(norm_sqr) -> MovingAvg<n>::new(decay, history) of examples/spectrum/src/bin/cpu.rs:21-28 in ONE pass over the
+// samples (b2s_spectrum_*); counts follow MovingAvg::work, values agree with the three blocks to rounding.
+class SpectrumPipe {
+public:
+    SpectrumPipe(const Instance &inst, size_t n, float decay_factor, size_t history_size, bool fft_shift = true,
+                 float log10_scale = 0.0f)
+        : input(inst), output(inst), inst_(inst), n_(n) {
+        check(b2s_spectrum_plan(inst.get(), n, fft_shift ? 1 : 0, decay_factor, history_size, log10_scale, &h_), inst.get());
+    }
+    ~SpectrumPipe() { b2s_spectrum_destroy(h_); }
+    void work(WorkIo &io) {
+        const size_t n = input.len();
+        size_t c = 0, p = 0;
+        check(b2s_spectrum_exec(h_, input.slice(), n, output.slice(), output.capacity(), &c, &p), inst_.get());
+        if (input.finished() && c / n_ == n / n_) io.finished = true;               // moving_avg.rs:106-108
+        input.consume(c); output.produce(p);
+    }
+    Reader<Complex32> input;
+    Writer<float> output;
+private:
+    const Instance &inst_; size_t n_; b2s_spectrum *h_ = nullptr;
+};
+
 // ≙ runtime::mocker::Mocker (mocker.rs:33-190): run one block without a scheduler
 template <typename Block> class Mocker {
 public:

@@ -212,6 +212,26 @@ int main() {
         try { MovingAvg bad(inst, 4, 1.5f, 2); } catch (const Error &) { threw = true; }
         CHECK(threw);                                                    // assert!((0.0..=1.0).contains(&decay_factor))
     }
+    {   // SpectrumPipe: a tone at +N/4 cycles/sample lands in bin N/2 + N/4 after the fftshift; 3 frames -> 1 row
+        const size_t N = 64, frames = 6;
+        SpectrumPipe sp(inst, N, 0.5f, 3);
+        std::vector<Complex32> in(N * frames);
+        for (size_t i = 0; i < in.size(); i++) {
+            const double ph = 2.0 * 3.14159265358979323846 * 0.25 * (double)i;
+            in[i] = Complex32((float)std::cos(ph), (float)std::sin(ph));
+        }
+        Mocker m(sp);
+        m.input(in);
+        m.init_output(N * 4);
+        m.run();
+        auto v = m.output();
+        CHECK(v.size() == 2 * N);                                        // 6 frames, one row every 3
+        size_t peak = 0;
+        for (size_t i = 0; i < N && i < v.size(); i++) if (v[N + i] > v[N + peak]) peak = i;
+        CHECK(peak == N / 2 + N / 4);
+        // |X|^2 = N^2 at the tone; avg after 6 frames with decay 0.5 = N^2 * (1 - 0.5^6)
+        if (v.size() == 2 * N) CHECK(std::fabs(v[N + peak] - (float)(N * N) * (1.0f - 0.015625f)) <= 1e-3f * N * N);
+    }
     std::printf(failures ? "C++ host layer: %d FAILURES\n" : "C++ host layer: all checks passed\n", failures);
     return failures ? 1 : 0;
 }
