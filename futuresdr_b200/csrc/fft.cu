@@ -31,6 +31,11 @@ struct b2s_fft {
     int log2m = 0;              // M = 2^log2m >= 2n - 1
     float2 *d_chirp = nullptr;  // w[k] = exp(-i pi k^2 / n), k in [0, n)
     float2 *d_bhat = nullptr;   // FFT_M of the wrapped conjugate chirp, pre-divided by M
+    // LARGE transforms (n > 16384, or Bluestein with M > 16384): four-step through HBM on top of two shared-memory plans
+    bool big = false;
+    size_t big_m = 0, big_n1 = 0, big_n2 = 0;     // M = n1 * n2 (M = n for powers of two)
+    b2s_fft *sub1 = nullptr, *sub2 = nullptr;     // forward n1- and n2-point plans (no shift, no scale)
+    float2 *d_work = nullptr;                     // 2 * M (four-step scratch) [+ 2 * M for Bluestein]
 };
 
 namespace {
@@ -247,9 +252,123 @@ int32_t launch_bluestein(b2s_fft *p, const BsArgs &a, cudaStream_t stream) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// LARGE transforms: rustfft plans any length (src/blocks/fft.rs:98-103); beyond what one shared-memory transform holds
+// the classic four-step algorithm runs through HBM:  M = n1 * n2,  i = i1*n2 + i2,  k = k1 + n1*k2,
+//   X[k1 + n1*k2] = sum_{i2} W_{n2}^{i2 k2} * ( W_M^{i2 k1} * sum_{i1} x[i1*n2 + i2] W_{n1}^{i1 k1} )
+// as  transpose -> n2 transforms of length n1 -> twiddle + transpose -> n1 transforms of length n2 -> transpose,
+// every transform being the batched shared-memory kernel above.  Five passes over the data instead of one: this path
+// exists for completeness (spectrum analysers with 64 Ki+ bins, odd lengths), not for speed.
+// ---------------------------------------------------------------------------------------------------------------
+struct BigT {                 // dst[c * R + r] = f(src[r * C + c]) with optional index rotations / twiddle / scale
+    const float2 *src;
+    float2 *dst;
+    long long R, C, M;
+    int conj_in, conj_out, twiddle;
+    long long src_rot, dst_rot;   // src index (idx + src_rot) % M ; dst index (idx + dst_rot) % M
+    float scale;
+};
+
+__global__ void big_transpose_kernel(const BigT a) {
+    __shared__ float2 tile[32][33];
+    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long r = r0 + i, c = c0 + threadIdx.x;
+        if (r < a.R && c < a.C) {
+            long long idx = r * a.C + c;
+            if (a.src_rot) { idx += a.src_rot; if (idx >= a.M) idx -= a.M; }
+            float2 v = a.src[idx];
+            if (a.conj_in) v.y = -v.y;
+            if (a.twiddle) {                                  // W_M^{r c}, exponent reduced exactly, angle in f64
+                const unsigned long long t = ((unsigned long long)r * (unsigned long long)c) % (unsigned long long)a.M;
+                double sn, cs;
+                sincospi(-2.0 * (double)t / (double)a.M, &sn, &cs);
+                const float wr = (float)cs, wi = (float)sn;
+                v = make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+            }
+            tile[i][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long c = c0 + i, r = r0 + threadIdx.x;
+        if (r < a.R && c < a.C) {
+            float2 v = tile[threadIdx.x][i];
+            if (a.conj_out) v.y = -v.y;
+            v.x *= a.scale; v.y *= a.scale;
+            long long idx = c * a.R + r;
+            if (a.dst_rot) { idx += a.dst_rot; if (idx >= a.M) idx -= a.M; }
+            a.dst[idx] = v;
+        }
+    }
+}
+
+int32_t big_transpose(b2s_ctx *ctx, const BigT &a, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div((size_t)a.C, (size_t)32), (unsigned)ceil_div((size_t)a.R, (size_t)32));
+    big_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(a);
+    B2S_CHECK_LAUNCH(ctx);
+    return B2S_OK;
+}
+
+// Bluestein element-wise stages for M > 16384
+__global__ void big_bs_pre(const float2 *__restrict__ in, const float2 *__restrict__ chirp, float2 *a, long long n, long long M,
+                           int inverse, long long src_rot) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += stride) {
+        float2 v = make_float2(0.f, 0.f);
+        if (j < n) {
+            long long sidx = j + src_rot; if (sidx >= n) sidx -= n;
+            float2 x = in[sidx];
+            if (inverse) x.y = -x.y;
+            v = cmul(x, chirp[j]);
+        }
+        a[j] = v;
+    }
+}
+__global__ void big_bs_mul(float2 *A, const float2 *__restrict__ bhat, long long M) {   // A <- conj(A . Bhat): input of the inverse M-point FFT
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += stride) {
+        const float2 y = cmul(A[j], bhat[j]);
+        A[j] = make_float2(y.x, -y.y);
+    }
+}
+__global__ void big_bs_post(const float2 *__restrict__ c, const float2 *__restrict__ chirp, float2 *out, long long n, int inverse,
+                            long long dst_rot, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        float2 y = cmul(make_float2(c[k].x, -c[k].y), chirp[k]);      // conj closes the inverse M-point FFT
+        if (inverse) y.y = -y.y;
+        y.x *= scale; y.y *= scale;
+        long long d = k + dst_rot; if (d >= n) d -= n;
+        out[d] = y;
+    }
+}
+
 // plan internals for the kernels that embed an N-point transform (chan.cu's fused channelizer)
 const float2 *b2s_fft_twiddles(const b2s_fft *p) { return p ? p->d_tw : nullptr; }
-int b2s_fft_log2n(const b2s_fft *p) { return (p && !p->bluestein) ? p->log2n : -1; }
+int b2s_fft_log2n(const b2s_fft *p) { return (p && !p->bluestein && !p->big) ? p->log2n : -1; }
+
+// one M-point forward transform src -> dst through the four-step scratch (d_work[0 .. 2M))
+static int32_t big_fft(b2s_fft *p, const float2 *src, float2 *dst, int conj_in, int conj_out, long long src_rot,
+                       long long dst_rot, float scale, cudaStream_t st) {
+    b2s_ctx *ctx = p->ctx;
+    const long long M = (long long)p->big_m, n1 = (long long)p->big_n1, n2 = (long long)p->big_n2;
+    float2 *A = p->d_work, *B = p->d_work + M;
+    size_t c = 0, q = 0;
+    int32_t rc;
+    BigT t{};
+    t.M = M; t.scale = 1.0f;
+    t.src = src; t.dst = A; t.R = n1; t.C = n2; t.conj_in = conj_in; t.src_rot = src_rot;       // x[i1][i2] -> A[i2][i1]
+    if ((rc = big_transpose(ctx, t, st))) return rc;
+    if ((rc = b2s_fft_exec(p->sub1, A, (size_t)M, B, (size_t)M, &c, &q))) return rc;               // n2 transforms of length n1
+    t = BigT{}; t.M = M; t.scale = 1.0f;
+    t.src = B; t.dst = A; t.R = n2; t.C = n1; t.twiddle = 1;                                       // Y[i2][k1] W_M^{i2 k1} -> A[k1][i2]
+    if ((rc = big_transpose(ctx, t, st))) return rc;
+    if ((rc = b2s_fft_exec(p->sub2, A, (size_t)M, B, (size_t)M, &c, &q))) return rc;               // n1 transforms of length n2
+    t = BigT{}; t.M = M;
+    t.src = B; t.dst = dst; t.R = n1; t.C = n2; t.conj_out = conj_out; t.dst_rot = dst_rot; t.scale = scale;   // Z[k1][k2] -> X[k2*n1 + k1]
+    return big_transpose(ctx, t, st);
+}
 
 extern "C" {
 
@@ -259,12 +378,14 @@ int32_t b2s_fft_plan_c32(b2s_ctx *ctx, size_t n, int32_t inverse, int32_t fft_sh
     *out = nullptr;
     if (n < 2) return b2s_fail(ctx, B2S_EINVAL, "b2s_fft_plan_c32: n must be >= 2");
     const bool pow2 = (n & (n - 1)) == 0;
-    if (pow2 && n > 16384) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: n = %zu > 16384", n);
-    if (!pow2 && n > 8192)
-        return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: non-power-of-two n = %zu > 8192 (Bluestein needs M >= 2n-1 <= 16384)", n);
+    // one transform in shared memory up to 16384 points (Bluestein: M >= 2n-1 <= 16384); beyond that four-step
+    // through HBM, bounded by the scratch it needs (2 M / 4 M items)
+    const bool big = pow2 ? n > 16384 : n > 8192;
+    if (pow2 && n > ((size_t)1 << 26)) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: n = %zu > 2^26", n);
+    if (!pow2 && n > ((size_t)1 << 24)) return b2s_fail(ctx, B2S_EUNSUPPORTED, "b2s_fft_plan_c32: non-power-of-two n = %zu > 2^24", n);
     DeviceGuard g(ctx->device);
     b2s_fft *p = new b2s_fft();
-    p->ctx = ctx; p->n = n;
+    p->ctx = ctx; p->n = n; p->big = big;
     p->inverse = inverse != 0; p->shift = fft_shift != 0; p->has_norm = has_normalize != 0; p->norm = normalize;
     const double PI = 3.14159265358979323846264338327950288;
     size_t tw_n = n;
@@ -275,14 +396,28 @@ int32_t b2s_fft_plan_c32(b2s_ctx *ctx, size_t n, int32_t inverse, int32_t fft_sh
         while (((size_t)1 << p->log2m) < 2 * n - 1) p->log2m++;
         tw_n = (size_t)1 << p->log2m;
     }
-    std::vector<float2> tw(tw_n);
-    for (size_t k = 0; k < tw_n; k++) {
+    if (big) {
+        // M = n1 * n2 with both factors <= 16384; the two shared-memory plans do the actual transforms
+        p->big_m = tw_n;
+        int l2 = 0;
+        while (((size_t)1 << l2) < tw_n) l2++;
+        p->big_n1 = (size_t)1 << ((l2 + 1) / 2);
+        p->big_n2 = tw_n / p->big_n1;
+        int32_t rc = b2s_fft_plan_c32(ctx, p->big_n1, 0, 0, 0, 1.0f, &p->sub1);
+        if (rc == B2S_OK) rc = b2s_fft_plan_c32(ctx, p->big_n2, 0, 0, 0, 1.0f, &p->sub2);
+        if (rc != B2S_OK) { b2s_fft_destroy(p); return rc; }
+        if (cudaMalloc((void **)&p->d_work, (p->bluestein ? 4 : 2) * tw_n * sizeof(float2)) != cudaSuccess) {
+            cudaGetLastError(); b2s_fft_destroy(p); return b2s_fail(ctx, B2S_ENOMEM, "fft four-step scratch (%zu items)", (p->bluestein ? 4 : 2) * tw_n);
+        }
+    }
+    std::vector<float2> tw(big ? 1 : tw_n);
+    for (size_t k = 0; k < tw.size(); k++) {
         const double ang = -2.0 * PI * (double)k / (double)tw_n;
         tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
-    cudaError_t e = cudaMalloc((void **)&p->d_tw, tw_n * sizeof(float2));
-    if (e != cudaSuccess) { delete p; return b2s_fail(ctx, B2S_ENOMEM, "fft twiddles"); }
-    B2S_CUDA(ctx, cudaMemcpyAsync(p->d_tw, tw.data(), tw_n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = cudaMalloc((void **)&p->d_tw, tw.size() * sizeof(float2));
+    if (e != cudaSuccess) { b2s_fft_destroy(p); return b2s_fail(ctx, B2S_ENOMEM, "fft twiddles"); }
+    B2S_CUDA(ctx, cudaMemcpyAsync(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<float2> chirp, bhat;
     if (p->bluestein) {
         const size_t M = tw_n;
@@ -333,6 +468,9 @@ void b2s_fft_destroy(b2s_fft *p) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_chirp) cudaFree(p->d_chirp);
     if (p->d_bhat) cudaFree(p->d_bhat);
+    if (p->d_work) cudaFree(p->d_work);
+    if (p->sub1) b2s_fft_destroy(p->sub1);
+    if (p->sub2) b2s_fft_destroy(p->sub2);
     delete p;
 }
 
@@ -349,6 +487,34 @@ int32_t b2s_fft_exec(b2s_fft *p, const void *d_in, size_t n_in, void *d_out, siz
     if (!d_in || !d_out) return b2s_fail(p->ctx, B2S_EINVAL, "b2s_fft_exec: NULL buffer");
     if (d_in == d_out) return b2s_fail(p->ctx, B2S_EINVAL, "b2s_fft_exec: in-place is not supported");
     DeviceGuard g(p->ctx->device);
+    if (p->big) {
+        cudaStream_t st = p->ctx->stream;
+        const long long n = (long long)p->n, M = (long long)p->big_m, half = n / 2;
+        const float scale = p->has_norm ? p->norm : 1.0f;
+        const int gridE = p->ctx->sm_count * 8;
+        for (size_t fr = 0; fr < m / p->n; fr++) {
+            const float2 *in = (const float2 *)d_in + fr * p->n;
+            float2 *out = (float2 *)d_out + fr * p->n;
+            int32_t rc;
+            if (!p->bluestein) {
+                // inverse = conj o FFT o conj; shift: pre-rotation for the inverse, post-rotation for the forward transform
+                rc = big_fft(p, in, out, p->inverse, p->inverse, (p->inverse && p->shift) ? half : 0,
+                             (!p->inverse && p->shift) ? half : 0, scale, st);
+                if (rc) return rc;
+                continue;
+            }
+            float2 *b0 = p->d_work + 2 * M, *b1 = p->d_work + 3 * M;
+            big_bs_pre<<<gridE, 256, 0, st>>>(in, p->d_chirp, b0, n, M, p->inverse, (p->inverse && p->shift) ? half : 0);
+            B2S_CHECK_LAUNCH(p->ctx);
+            if ((rc = big_fft(p, b0, b1, 0, 0, 0, 0, 1.0f, st))) return rc;
+            big_bs_mul<<<gridE, 256, 0, st>>>(b1, p->d_bhat, M);
+            B2S_CHECK_LAUNCH(p->ctx);
+            if ((rc = big_fft(p, b1, b0, 0, 0, 0, 0, 1.0f, st))) return rc;
+            big_bs_post<<<gridE, 256, 0, st>>>(b0, p->d_chirp, out, n, p->inverse, (!p->inverse && p->shift) ? n - half : 0, scale);
+            B2S_CHECK_LAUNCH(p->ctx);
+        }
+        return B2S_OK;
+    }
     if (p->bluestein) {
         BsArgs b;
         b.in = (const float2 *)d_in; b.out = (float2 *)d_out; b.tw = p->d_tw; b.chirp = p->d_chirp; b.bhat = p->d_bhat;

@@ -123,39 +123,35 @@ __global__ void __launch_bounds__(kSpThreads, (LOG2N <= 12 ? 3 : 1)) spectrum_ke
     }
 }
 
-// Carry scan across the groups + fix-up of the emitted rows, one kernel.  A CTA owns 32 adjacent bins (the lanes of
-// a warp: every load / store below is one coalesced 128-byte line) and cuts the groups into 32 segments, one per warp:
+// Carry scan across the groups.  A CTA owns 32 adjacent bins (the lanes of a warp: every load / store below is one
+// coalesced 128-byte line) and cuts the groups into 32 segments, one per warp:
 //   1. each warp composes the affine maps  x -> final_g + A_g * x  of its segment (sequential over ~groups/32 groups);
 //   2. the 32 composites of a bin are scanned through shared memory (sequential over segments, 32 lanes = 32 bins);
-//   3. each warp walks its segment again with the now known incoming state: it records nothing but FIXES the rows its
-//      groups emitted,  out[row][bin] += a^k * carry_g[bin]  (+ the optional k*log10), and the last warp leaves the
-//      state after the call in avg[].
-// (The first version gave a warp to each bin with the lanes striding over groups: 4-byte loads 8 KiB apart, 207 us for
-// 7 MB of carries -- as long as the FFT kernel itself -- plus an 88 us element-wise fix-up kernel with a 64-bit
-// division per element.)
+//   3. each warp walks its segment again with the now known incoming state and overwrites fin[g][bin] with the state
+//      group g STARTS from; the state after the call goes to avg[].
+// (History: a warp per bin with the lanes striding over groups -- 4-byte loads 8 KiB apart -- took 207 us for 7 MB of
+// carries, as long as the FFT kernel itself; doing the row fix-up inside step 3 left ~200 dependent memory round trips
+// per warp and took 224 us.  Carries and fix-up are separate again, each fully parallel.)
 constexpr int kScanSegs = 32;
 __global__ void __launch_bounds__(32 * kScanSegs)
-spectrum_scan_fixup(const float *__restrict__ fin, float *avg, float *out, const float *__restrict__ apow, int n, int groups,
-                    long long C, long long nframes, int history, int i0, float A, float A_last, float log10_k) {
+spectrum_scan(float *fin, float *avg, int n, int groups, float A, float A_last) {
     __shared__ float sL[kScanSegs][33], sM[kScanSegs][33], sX[kScanSegs][33];
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int bin = blockIdx.x * 32 + lane;
     const bool live = bin < n;
     const int per = (groups + kScanSegs - 1) / kScanSegs;
     const int g0 = min(seg * per, groups), g1 = min(g0 + per, groups);
-    // 1. compose this segment
     float L = 0.0f, M = 1.0f;
     if (live) {
 #pragma unroll 4
         for (int g = g0; g < g1; g++) {
             const float Ag = (g == groups - 1) ? A_last : A;
-            L = fmaf(Ag, L, __ldg(fin + (size_t)g * n + bin));
+            L = fmaf(Ag, L, fin[(size_t)g * n + bin]);
             M *= Ag;
         }
     }
     sL[seg][lane] = L; sM[seg][lane] = M;
     __syncthreads();
-    // 2. warp 0: state entering every segment of its 32 bins
     if (seg == 0) {
         float x = live ? avg[bin] : 0.0f;
         for (int sgm = 0; sgm < kScanSegs; sgm++) {
@@ -165,23 +161,33 @@ spectrum_scan_fixup(const float *__restrict__ fin, float *avg, float *out, const
         if (live) avg[bin] = x;                              // state after the call
     }
     __syncthreads();
-    // 3. walk the segment again: fix the rows each group emitted
     if (!live) return;
     float x = sX[seg][lane];
+#pragma unroll 4
     for (int g = g0; g < g1; g++) {
         const float Ag = (g == groups - 1) ? A_last : A;
-        const long long fb = (long long)g * C, fe = min(fb + C, nframes);
-        // first frame of the group that emits: (i0 + f + 1) % history == 0
-        long long f = fb + ((history - (int)((i0 + fb + 1) % history)) % history);
-        for (; f < fe; f += history) {
-            const long long row = (i0 + f + 1) / history - 1;
-            float *o = out + row * n + bin;
-            float v = fmaf(apow[f - fb + 1], x, *o);
-            if (log10_k != 0.0f) v = log10_k * log10f(v);
-            *o = v;
-        }
-        x = fmaf(Ag, x, __ldg(fin + (size_t)g * n + bin));
+        const float f = fin[(size_t)g * n + bin];
+        fin[(size_t)g * n + bin] = x;                        // carry INTO group g
+        x = fmaf(Ag, x, f);
     }
+}
+
+// emitted[row] += a^k * carry_g  (k = frames of group g up to and including the emitting one), then the optional
+// k*log10.  One row (or a 1024-bin slice of it) per CTA: the group / power look-up is per CTA, accesses are float4.
+__global__ void __launch_bounds__(256)
+spectrum_fixup(float *out, const float *__restrict__ carry, const float *__restrict__ apow, int n, long long C,
+               int history, int i0, float log10_k) {
+    const long long row = blockIdx.x;
+    const long long f = (row + 1) * history - i0 - 1;          // frame (within the call) that emitted this row
+    const long long g = f / C;
+    const float w = apow[(int)(f - g * C) + 1];
+    const int b = (blockIdx.y * 256 + threadIdx.x) * 4;
+    if (b >= n) return;
+    float4 v = *reinterpret_cast<float4 *>(out + row * n + b);
+    const float4 c = *reinterpret_cast<const float4 *>(carry + (size_t)g * n + b);
+    v.x = fmaf(w, c.x, v.x); v.y = fmaf(w, c.y, v.y); v.z = fmaf(w, c.z, v.z); v.w = fmaf(w, c.w, v.w);
+    if (log10_k != 0.0f) { v.x = log10_k * log10f(v.x); v.y = log10_k * log10f(v.y); v.z = log10_k * log10f(v.z); v.w = log10_k * log10f(v.w); }
+    *reinterpret_cast<float4 *>(out + row * n + b) = v;
 }
 
 template <int LOG2N>
@@ -280,7 +286,8 @@ int32_t b2s_spectrum_exec(b2s_spectrum *p, const void *d_in, size_t n_in, void *
     *consumed = frames * N; *produced = rows * N;
     if (frames == 0) return B2S_OK;
     if (!d_in || (rows && !d_out)) return b2s_fail(ctx, B2S_EINVAL, "b2s_spectrum_exec: NULL buffer");
-    if (reinterpret_cast<uintptr_t>(d_in) & 15) return b2s_fail(ctx, B2S_EINVAL, "b2s_spectrum_exec: the input slice must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (rows && (reinterpret_cast<uintptr_t>(d_out) & 15)))
+        return b2s_fail(ctx, B2S_EINVAL, "b2s_spectrum_exec: the input and output slices must be 16-byte aligned");
     DeviceGuard g(ctx->device);
     NvtxRange nvtx("b2s_spectrum_exec");
     cudaStream_t st = ctx->stream;
@@ -343,10 +350,14 @@ int32_t b2s_spectrum_exec(b2s_spectrum *p, const void *d_in, size_t n_in, void *
     if (rc != B2S_OK) return rc == B2S_EUNSUPPORTED ? b2s_fail(ctx, rc, "b2s_spectrum_exec: unsupported size") : rc;
     const double ad = (double)(1.0f - p->decay);
     const size_t c_last = frames - (groups - 1) * C;
-    spectrum_scan_fixup<<<(unsigned)ceil_div(N, (size_t)32), 32 * kScanSegs, 0, st>>>(
-        p->d_final, p->d_avg, (float *)d_out, p->d_pow, (int)N, (int)groups, (long long)C, (long long)frames, (int)h,
-        (int)p->i, (float)std::pow(ad, (double)C), (float)std::pow(ad, (double)c_last), p->log10_k);
+    spectrum_scan<<<(unsigned)ceil_div(N, (size_t)32), 32 * kScanSegs, 0, st>>>(
+        p->d_final, p->d_avg, (int)N, (int)groups, (float)std::pow(ad, (double)C), (float)std::pow(ad, (double)c_last));
     B2S_CHECK_LAUNCH(ctx);
+    if (rows) {
+        dim3 grid((unsigned)rows, (unsigned)ceil_div(N, (size_t)1024));
+        spectrum_fixup<<<grid, 256, 0, st>>>((float *)d_out, p->d_final, p->d_pow, (int)N, (long long)C, (int)h, (int)p->i, p->log10_k);
+        B2S_CHECK_LAUNCH(ctx);
+    }
     p->i = (p->i + frames) % h;
     return B2S_OK;
 }

@@ -173,7 +173,11 @@ int32_t b2s_pfbarb_exec(b2s_pfbarb *p, const void *d_in, size_t n_in, void *d_ou
 /* ---- FFT (≙ Fft::with_options, src/blocks/fft.rs:66-121, and Fft::work :160-221) ---------
  * inverse: FftDirection; fft_shift, normalize as in with_options (has_normalize = Option::is_some).
  * One exec processes m = floor(min(n_in, n_out_cap)/n)*n items (no 32-FFT cap: the cap only
- * splits work across calls, fft.rs:171). */
+ * splits work across calls, fft.rs:171).
+ * Lengths: any n >= 2 like rustfft.  Powers of two <= 16384 and other lengths <= 8192 run as ONE pass through shared
+ * memory (Stockham / fused Bluestein: 16 B/sample of HBM traffic); larger ones -- powers of two up to 2^26, other
+ * lengths up to 2^24 -- use the four-step algorithm through HBM on top of two shared-memory plans (five passes;
+ * the plan owns 2 n / 4 M items of scratch).  Changing the length = destroy + create (fft.rs:124-151's handler). */
 int32_t b2s_fft_plan_c32(b2s_ctx *ctx, size_t n, int32_t inverse, int32_t fft_shift,
                          int32_t has_normalize, float normalize, b2s_fft **out);
 void    b2s_fft_destroy(b2s_fft *f);

@@ -145,11 +145,54 @@ def test_fft_roundtrip_and_parseval_full_size(fb):
 def test_fft_unsupported_sizes_fail_loudly(fb):
     from futuresdr_b200.blocks import Fft
     with pytest.raises(fb.B200SdrError):
-        Fft(10000)                      # non-power-of-two beyond the Bluestein limit (8192)
+        Fft((1 << 24) + 1)              # non-power-of-two beyond the four-step Bluestein scratch limit
     with pytest.raises(fb.B200SdrError):
-        Fft(32768)
+        Fft(1 << 27)
     with pytest.raises(fb.B200SdrError):
         Fft(1)
+
+
+def _fft_block_numpy(x, n, inverse, shift, norm):
+    """Fft::work (fft.rs:160-221) with numpy's pocketfft in double precision as the transform: the reference for
+    lengths the oracle's direct O(n^2) DFT cannot reach in test time."""
+    m = (x.size // n) * n
+    fr = x[:m].astype(np.complex128).reshape(-1, n)
+    if inverse and shift:
+        fr = np.roll(fr, -(n // 2), axis=1)                    # buff[k] = i[(k + n/2) % n]   (:179-185)
+    X = np.fft.ifft(fr, axis=1) * n if inverse else np.fft.fft(fr, axis=1)
+    if not inverse and shift:
+        X = np.roll(X, -(n // 2), axis=1)                      # o[k] = X[(k + n/2) % n]      (:196-204)
+    if norm is not None:
+        X = X * np.float32(norm)
+    return m, X.reshape(-1)
+
+
+@pytest.mark.parametrize("n", [32768, 65536, 1 << 20, 8193, 10007, 12000, 100003])
+def test_fft_large_sizes_four_step(fb, rng, n):
+    """rustfft plans ANY length (fft.rs:98-103).  Beyond one shared-memory transform (16384 points, 8192 for other
+    lengths) the four-step algorithm runs through HBM on top of two shared-memory plans, with Bluestein on top of
+    that for lengths that are not powers of two (10007 and 100003 are prime)."""
+    import torch
+    from futuresdr_b200.blocks import Fft, FftDirection
+    nfft = 2
+    x = _noise(rng, n * nfft + 3)
+    for inverse, shift, norm in ((False, False, None), (False, True, None), (True, True, 1.0 / n), (True, False, None)):
+        fft = Fft.with_options(n, FftDirection.Inverse if inverse else FftDirection.Forward, shift, norm)
+        out = torch.zeros(x.size, dtype=torch.complex64, device="cuda")
+        m = fft.transform(_dev(x), out)
+        torch.cuda.synchronize()
+        m0, ref = _fft_block_numpy(x, n, inverse, shift, norm)
+        assert m == m0 == n * nfft
+        got, r = out[:m].cpu().numpy().reshape(nfft, n), ref.reshape(nfft, n)
+        assert np.all(np.max(np.abs(got - r), axis=1) <= 1e-5 * np.max(np.abs(r), axis=1)), (n, inverse, shift)
+    if n in (32768, 8193):                                     # and the oracle itself on the sizes it can afford
+        m0, ref = orc.fft_block(x, n, fft_shift=True)
+        fft = Fft.with_options(n, FftDirection.Forward, True, None)
+        out = torch.zeros(x.size, dtype=torch.complex64, device="cuda")
+        fft.transform(_dev(x), out)
+        torch.cuda.synchronize()
+        got, r = out[:m0].cpu().numpy().reshape(nfft, n), ref.reshape(nfft, n)
+        assert np.all(np.max(np.abs(got - r), axis=1) <= 1e-5 * np.max(np.abs(r), axis=1))
 
 
 @pytest.mark.parametrize("n", [3, 5, 6, 7, 12, 100, 1000, 1536, 4095, 5000, 8191])
