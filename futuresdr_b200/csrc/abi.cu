@@ -286,6 +286,7 @@ int32_t b2s_fir_exec(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, siz
     if (*produced == 0) return B2S_OK;
     if (!d_in || !d_out) return b2s_fail(f->ctx, B2S_EINVAL, "b2s_fir_exec: NULL buffer");
     DeviceGuard g(f->ctx->device);
+    NvtxRange nvtx("b2s_fir_exec");
     return fir_launch(f, d_in, n_in, d_out, *produced, f->ctx->stream);
 }
 
@@ -386,6 +387,7 @@ int32_t b2s_fir_exec_hist(b2s_fir *f, const void *d_hist, size_t n_hist, const v
     if (n_hist && !d_hist) return b2s_fail(ctx, B2S_EINVAL, "b2s_fir_exec_hist: NULL history");
     fir_counts(f, n_hist + n_in, n_out_cap, consumed, produced, status);
     DeviceGuard g(ctx->device);
+    NvtxRange nvtx("b2s_fir_exec_hist");
     cudaStream_t st = ctx->stream;
     FirHist h;
     h.d_hist = d_hist; h.n_hist = n_hist;

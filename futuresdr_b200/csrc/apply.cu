@@ -149,6 +149,7 @@ int32_t b2s_apply_exec(b2s_apply *a, const void *d_in, size_t n_in, void *d_out,
             return b2s_fail(a->ctx, B2S_EINVAL, "b2s_apply_exec: the quadrature demodulator cannot run in place (input and output overlap)");
     }
     DeviceGuard g(a->ctx->device);
+    NvtxRange nvtx("b2s_apply_exec");
     int32_t rc = B2S_EINVAL;
     switch (a->op) {
         case B2S_OP_SCALE_F32: rc = launch<B2S_OP_SCALE_F32>(a, d_in, d_out, m); break;

@@ -230,6 +230,13 @@ __global__ void chan_transpose_kernel(const float2 *__restrict__ spec, float2 *_
 // Outputs whose windows still reach into the previous call's history (the first T-1 of a call) take the generic
 // three-kernel path.
 // ---------------------------------------------------------------------------------------------------------------
+// Row stride of the FFT buffers.  The padded index idx + idx/16 needs N + N/16 - 1 slots; using exactly that (an ODD
+// number of float2 for N >= 32) also spreads the 512/N transforms a warp works on over distinct bank offsets -- with
+// the round figure N + N/16 = 68 (N = 64) rows start only 8 banks apart and the 8 transforms x 4 threads of a warp
+// share 8 bank pairs (ncu: 17 M store conflicts on 30 M store wavefronts).  It also keeps the 64-channel kernel at
+// EXACTLY two CTAs per SM: 2 x (2 x 40448 + 64 x 67 x 8 + 1024 reserved) <= 233472 bytes.
+__host__ __device__ constexpr int chan_row_stride(int n) { return n >= 16 ? n + n / 16 - 1 : n + 1; }
+
 __device__ __forceinline__ void chan_cp_async16(void *dst_smem, const void *src, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
     const int sz = valid ? 16 : 0;                       // src-size 0: the 16 bytes are zero-filled
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(256) chan_fused_kernel(const float2 *__restric
     constexpr int RUNS = 256 / N;                            // runs of outputs per window
     constexpr int RL = OB / RUNS;                            // outputs per run
     constexpr int ROWS = OB + TPAD - 1;
-    constexpr int NP = N + N / 16;
+    constexpr int NP = chan_row_stride(N);
     constexpr size_t XCAP = ((size_t)ROWS * N > (size_t)OB * (N + 1)) ? (size_t)ROWS * N : (size_t)OB * (N + 1);
     extern __shared__ __align__(16) unsigned char csm[];
     float2 *Xbuf = reinterpret_cast<float2 *>(csm);          // 2 x [ROWS][N] input tiles (each reused as the transposed staging [OB][N+1])
@@ -334,7 +341,7 @@ template <int LOG2N, int TPAD> constexpr size_t chan_fused_smem() {
     constexpr int TT = (N / 16 < 1) ? 1 : N / 16;
     constexpr int OB = 256 / TT;
     constexpr size_t xcap = ((size_t)(OB + TPAD - 1) * N > (size_t)OB * (N + 1)) ? (size_t)(OB + TPAD - 1) * N : (size_t)OB * (N + 1);
-    return (2 * xcap + (size_t)OB * (N + N / 16)) * sizeof(float2);
+    return (2 * xcap + (size_t)OB * chan_row_stride(N)) * sizeof(float2);
 }
 
 static inline bool ntiles_overflow(long long nprod, long long o_first, int ob) { return (nprod - o_first) / ob > 0x7fffff00ll; }

@@ -487,6 +487,7 @@ int32_t b2s_fft_exec(b2s_fft *p, const void *d_in, size_t n_in, void *d_out, siz
     if (!d_in || !d_out) return b2s_fail(p->ctx, B2S_EINVAL, "b2s_fft_exec: NULL buffer");
     if (d_in == d_out) return b2s_fail(p->ctx, B2S_EINVAL, "b2s_fft_exec: in-place is not supported");
     DeviceGuard g(p->ctx->device);
+    NvtxRange nvtx("b2s_fft_exec");
     if (p->big) {
         cudaStream_t st = p->ctx->stream;
         const long long n = (long long)p->n, M = (long long)p->big_m, half = n / 2;

@@ -149,6 +149,7 @@ int32_t b2s_mavg_exec(b2s_mavg *m, const void *d_in, size_t n_in, void *d_out, s
     if (c == 0) return B2S_OK;
     if (!d_in || (!d_out && p)) return b2s_fail(m->ctx, B2S_EINVAL, "b2s_mavg_exec: NULL buffer");
     DeviceGuard g(m->ctx->device);
+    NvtxRange nvtx("b2s_mavg_exec");
     mavg_kernel<<<(unsigned)ceil_div(W, (size_t)kMaBins), 32 * kMaWarps, 0, m->ctx->stream>>>(
         (const float *)d_in, (float *)d_out, m->d_avg, (int)W, (long long)c, (int)m->history, (int)m->i, m->decay,
         (long long)p);

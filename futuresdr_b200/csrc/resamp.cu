@@ -145,6 +145,7 @@ int32_t b2s_resamp_exec(b2s_resamp *r, const void *d_in, size_t n_in, void *d_ou
     if (p == 0) return B2S_OK;
     if (!d_in || !d_out) return b2s_fail(ctx, B2S_EINVAL, "b2s_resamp_exec: NULL buffer");
     DeviceGuard g(ctx->device);
+    NvtxRange nvtx("b2s_resamp_exec");
     if (r->d_gtab)   // small L*M: L decimate-by-M sliding-window passes over one staged tile (fir_direct.cu)
         return resamp_slide_launch(ctx, r->kind, r->d_gtab, L, M, T, d_in, n_in, d_out, p, ctx->stream);
     const size_t isz = kind_in_bytes(r->kind);

@@ -171,6 +171,7 @@ int32_t b2s_synth_exec(b2s_synth *s, const void *d_in, size_t in_stride, size_t 
     if (nv == 0) return B2S_OK;
     if (!d_in || (!d_out && p)) return b2s_fail(ctx, B2S_EINVAL, "b2s_synth_exec: NULL buffer");
     DeviceGuard g(ctx->device);
+    NvtxRange nvtx("b2s_synth_exec");
     const size_t items = nv * N;
     if (s->tmp_items < items) {
         B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
