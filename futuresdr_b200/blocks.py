@@ -200,6 +200,26 @@ class Fft(Block):
     def with_options(cls, len, direction, fft_shift, normalize):
         return cls(len, direction, fft_shift, normalize)
 
+    def fft_size(self, p=None):
+        """The `fft_size` message handler (fft.rs:124-136): an integer re-plans (`set_fft_size`, :139-151) and answers
+        "Ok"; ``None`` (Pmt::Null) answers the current length; anything else "InvalidValue"."""
+        if p is None:
+            return self.len
+        if isinstance(p, (int, np.integer)) and not isinstance(p, bool):
+            self.set_fft_size(int(p))
+            return "Ok"
+        return "InvalidValue"
+
+    def set_fft_size(self, new_len: int):
+        """Fft::set_fft_size (fft.rs:139-151): a new plan of the same direction / shift / normalisation.  The new plan is
+        built first, so a length this build cannot plan leaves the block as it was."""
+        h = C.c_void_p()
+        check(lib.b2s_fft_plan_c32(self.ctx.handle, int(new_len), int(self.direction == FftDirection.Inverse),
+                                   int(self.fft_shift), int(self.normalize is not None), float(self.normalize or 0.0),
+                                   C.byref(h)), self.ctx.handle)
+        lib.b2s_fft_destroy(self._h)
+        self._h, self.len = h, int(new_len)
+
     def transform(self, i: torch.Tensor, o: torch.Tensor):
         """The body of Fft::work on explicit slices. Returns m (= consumed = produced)."""
         c, p = C.c_size_t(0), C.c_size_t(0)

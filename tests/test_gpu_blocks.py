@@ -152,6 +152,27 @@ def test_fft_unsupported_sizes_fail_loudly(fb):
         Fft(1)
 
 
+def test_fft_size_handler_replans(fb, rng):
+    """The `fft_size` message handler (fft.rs:124-151): a new length takes effect for the next work() call, keeping
+    direction / shift / normalisation; Null answers the length; other values are refused."""
+    import torch
+    from futuresdr_b200.blocks import Fft, FftDirection
+    fft = Fft.with_options(1024, FftDirection.Forward, True, 0.5)
+    assert fft.fft_size() == 1024
+    assert fft.fft_size("x") == "InvalidValue" and fft.fft_size() == 1024
+    assert fft.fft_size(3000) == "Ok" and fft.fft_size() == 3000
+    x = _noise(rng, 3000 * 4)
+    out = torch.zeros(x.size, dtype=torch.complex64, device="cuda")
+    assert fft.transform(_dev(x), out) == x.size
+    torch.cuda.synchronize()
+    m0, ref = _fft_block_numpy(x, 3000, False, True, 0.5)
+    got, r = out.cpu().numpy().reshape(4, 3000), ref.reshape(4, 3000)
+    assert np.all(np.max(np.abs(got - r), axis=1) <= 1e-5 * np.max(np.abs(r), axis=1))
+    with pytest.raises(fb.B200SdrError):
+        fft.set_fft_size(1)
+    assert fft.fft_size() == 3000                     # a refused length leaves the block as it was
+
+
 def _fft_block_numpy(x, n, inverse, shift, norm):
     """Fft::work (fft.rs:160-221) with numpy's pocketfft in double precision as the transform: the reference for
     lengths the oracle's direct O(n^2) DFT cannot reach in test time."""
