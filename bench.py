@@ -526,10 +526,11 @@ def sec_ring_vulkan(torch, fb, dev, args):
 
 def _fm_chain(torch, fb, dev):
     from futuresdr_b200 import blocks as B
-    import oracle as orc
     dec = B.FirBuilder.decimating(4)
     dem = B.Apply(B.ApplyOp.QuadDemodC32)
-    ptaps = (orc.kaiser_lowpass(0.4 / 32, 0.1 / 32, 1e-3) * 32).astype(np.float32)[: 32 * 16]
+    # prototype low-pass of the resampler from the product's own tap design (b2s_firdes_*; bit-identical to the
+    # reference's firdes::kaiser::lowpass, tests/test_abi_symbols.py)
+    ptaps = (fb.firdes.kaiser.lowpass(0.4 / 32, 0.1 / 32, 1e-3) * 32).astype(np.float32)[: 32 * 16]
     pfb = B.PfbArbResampler(0.768, ptaps, 32)
     return dec, dem, pfb, ptaps
 
@@ -592,27 +593,24 @@ def sec_config3_fm_chain(torch, fb, dev, args, h_in, h_out):
     assert counts["decim"] == (total - 51) // 4, counts
     # algorithmic bytes per INPUT sample, fused ideal: 8 in + 8 * 0.768 / 4 out
     alg = total * (8 + 8 * 0.768 / 4)
-    # CPU twin on a bounded sample: same chain, oracle functions, one thread (PfbArb is a sequential state machine)
+    # cpu_baseline leg: the same chain with the oracle functions on a bounded sample -- the first 4 Mi samples of THIS
+    # run's input, one thread (PfbArb is a sequential state machine).  Its output doubles as the checker of the device
+    # chain on the same samples (counts exact, values compared).
     n_cpu = 4 * 1024 * 1024
-    xc = _cpu_noise(n_cpu)
+    xs = x[:n_cpu].cpu().numpy()
     dtaps = orc.kaiser_lowpass(0.25, 0.1, 1e-4)
     t0 = time.perf_counter()
-    _, _, _, dref = orc.decim_fir(dtaps, 4, xc, n_cpu)
-    ph, _ = orc.quad_demod(dref)
-    yref = orc.PfbArb(0.768, ptaps, 32).run(ph.astype(np.complex64), out_cap_per_call=1 << 22)
-    cpu_s = time.perf_counter() - t0
-    # parity spot check at the bench's own size: first chunk of the device chain against the oracle on its first 4 Mi inputs
-    pfb.reset(); dem.reset()
-    xs = x[:n_cpu].cpu().numpy()
     _, _, _, dref = orc.decim_fir(dtaps, 4, xs, n_cpu)
     ph, _ = orc.quad_demod(dref)
     yref = orc.PfbArb(0.768, ptaps, 32).run(ph.astype(np.complex64), out_cap_per_call=1 << 22)
+    cpu_s = time.perf_counter() - t0
+    pfb.reset(); dem.reset()
     p, o = chunk_work(x[:n_cpu], d3)
     torch.cuda.synchronize()
     ydev = d3[:o].cpu().numpy()
     parity = {"n_in": n_cpu, "count_match": bool(o == yref.size), "n_out": int(o),
               "max_abs_err": float(np.max(np.abs(ydev - yref[:o]))) if o else None,
-              "note": "device chain on the first 4 Mi samples of this run's input against the oracle chain; phases are O(pi)"}
+              "note": "device chain on the first 4 Mi samples of this run's input against the cpu_baseline run on the same samples; phases are O(pi)"}
     # end to end through host buffers: 64 Mi samples in 4 chunks of 16 Mi
     n_e = h_in.numel() - (h_in.numel() % 4)
     ce = 16 * 1024 * 1024
