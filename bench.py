@@ -975,6 +975,8 @@ def run_ours(args):
                     "api": "FirFilter.filter(host_in, host_out) -> b2s_fir_filter_host (pinned host, chunked H2D/kernel/D2H pipeline)",
                     "host_copy_ceiling": ceiling},
             "gpu_launches": int(launches),
+            "parity": {"headline": "pinned: FirFilter is checked against the reference's known-answer vectors (fir.rs:283-365) through the oracle and the C ABI; tolerance 1e-5 * ||taps||_1 * max|x|",
+                       "secondary": "configs[0], [4]: pinned (FIR).  configs[2] (PfbArbResampler, demod closure), configs[3] (Fft = rustfft, un-vendored), spectrum pipe, ring x12: parity UNPINNED -- the reference holds no value test; the oracle is a restatement of the cited lines"},
             "clocks": clocks,
             "per_rank": per_rank, "host_enqueue_us_per_step": host_step_us,
             "secondary": secondary,

@@ -68,13 +68,6 @@ __global__ void chan_hist_from_circ(const float2 *__restrict__ circ, const int *
     for (int t = threadIdx.x; t < T; t += blockDim.x) hist[(size_t)w * T + t] = circ[(size_t)w * 2 * T + s + t];
 }
 
-// j-th newest sample of window b when E = (o+1)*D samples of this call have been pushed
-__device__ __forceinline__ float2 chan_sample(const float2 *__restrict__ in, const float2 *__restrict__ hist,
-                                              int T, int N, long long c_new, int m, int b, int j) {
-    if (j < m) return __ldg(in + (c_new - (long long)j * N));
-    return hist[(size_t)b * T + (T - 1 - (j - m))];
-}
-
 // Critically sampled steady state (D == N, the window already holds T samples of this call): every output
 // pushes exactly one new sample into every window and the window keeps meeting the same arm, so the T samples
 // and the T taps live in REGISTERS; the output loop is unrolled T times so that the ring positions are static.
@@ -230,12 +223,12 @@ __global__ void chan_transpose_kernel(const float2 *__restrict__ spec, float2 *_
 // Outputs whose windows still reach into the previous call's history (the first T-1 of a call) take the generic
 // three-kernel path.
 // ---------------------------------------------------------------------------------------------------------------
-// Row stride of the FFT buffers.  The padded index idx + idx/16 needs N + N/16 - 1 slots; using exactly that (an ODD
-// number of float2 for N >= 32) also spreads the 512/N transforms a warp works on over distinct bank offsets -- with
-// the round figure N + N/16 = 68 (N = 64) rows start only 8 banks apart and the 8 transforms x 4 threads of a warp
-// share 8 bank pairs (ncu: 17 M store conflicts on 30 M store wavefronts).  It also keeps the 64-channel kernel at
-// EXACTLY two CTAs per SM: 2 x (2 x 40448 + 64 x 67 x 8 + 1024 reserved) <= 233472 bytes.
-__host__ __device__ constexpr int chan_row_stride(int n) { return n >= 16 ? n + n / 16 - 1 : n + 1; }
+// Row stride of the FFT buffers = the padded transform length.  (Tried: the exact, odd stride N + N/16 - 1, which puts
+// the 512/N transforms a warp works on at distinct bank offsets -- ncu counts 17 M store conflicts on 30 M store
+// wavefronts with 68 -- but rows that start 8 bytes off a 16-byte boundary cost more than the conflicts: 64 channels
+// 195 -> 182 Gsamples/s, 16 channels 262 -> 193.  Also: at 68 the 64-channel kernel sits at EXACTLY two CTAs per SM,
+// 2 x (2 x 40448 + 64 x 68 x 8 + 1024 reserved) = 233472 bytes; one float2 more per row halves the occupancy.)
+__host__ __device__ constexpr int chan_row_stride(int n) { return n + n / 16; }
 
 __device__ __forceinline__ void chan_cp_async16(void *dst_smem, const void *src, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);

@@ -54,10 +54,6 @@ struct SpArgs {
     float a, d;
 };
 
-__device__ __forceinline__ void sp_cp_async8(void *dst_smem, const void *src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-}
 __device__ __forceinline__ void sp_cp_async16(void *dst_smem, const void *src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");

@@ -10,3 +10,4 @@ print('value',d['value'],'ms',d['ms_per_step'],'frac',d['roofline']['frac'],'e2e
 for s in d['secondary']:
     print(s['config']['workload'][:60], '| value', s.get('value'), '| frac', (s.get('roofline') or {}).get('frac'), '| e2e', (s.get('e2e') or {}).get('value'), '|', (s.get('fused_spectrum_pipe') or {}).get('value'), s.get('error'))
 PY
+echo "--- small sweep"; timeout 600 python scripts/small_sweep.py 2>&1 | tail -10
