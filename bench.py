@@ -448,7 +448,7 @@ def sec_config1_perf_fir(torch, fb, dev, args):
         "cuda_graph": ({"value": pipes * n / graph_sec / 1e6, "unit": "Msamples/s", "ms_per_pass": graph_sec * 1e3,
                         "note": "the same pipes x stages launches captured once in a CUDA graph and replayed"}
                        if graph_sec else {"error": locals().get("graph_err")}),
-        "roofline": _roofline(8.0 * n * stages * pipes, min(sec, graph_sec or sec), "8 B/sample/stage; 30 launches of ~4 MB each: launch-latency bound (best of eager / graph replay)"),
+        "roofline": _roofline(8.0 * n * stages * pipes, min(sec, graph_sec or sec), "8 B/sample/stage; 30 launches of ~4 MB each: launch-latency bound (best of eager / graph replay); at this slice size AUTO runs the CUDA-core kernel (the tensor kernel's fixed cost is ~12 us per launch)"),
         "cpu_baseline": {"value": pipes * n / cpu_s / 1e6, "unit": "Msamples/s", "cores": pipes, "kind": "port",
                          "sample": "the whole config: 5 pipes x 6 stages x 1 M samples, oracle port of fir.rs:52-91 (strict order), one thread per pipe"},
         "e2e": {"value": pipes * n / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * n * pipes,

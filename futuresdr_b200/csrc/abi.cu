@@ -273,6 +273,15 @@ static void fir_counts(const b2s_fir *f, size_t n_in, size_t n_out_cap, size_t *
 static int32_t fir_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out, size_t n_out,
                           cudaStream_t stream) {
     if (f->kind == B2S_F64_F64) return fir_f64_launch(f, d_in, n_in, d_out, n_out, stream);
+    // SMALL slices under AUTO: the tensor kernel has a fixed cost of ~12 us per launch (TMEM allocation, Toeplitz fill,
+    // 148 persistent CTAs) against ~7 us for the CUDA-core kernel, whose time then grows with n_out * ntaps
+    // (scripts/small_sweep.py on B200: 6.9e-14 s per f32 sample-tap, 1.15e-13 per c32 one).  Below ~10 us of estimated
+    // CUDA-core time the direct form wins -- the perf/fir regime (1 M-sample calls of a 64-tap filter: 12.3 -> 7.3 us).
+    // An explicit B2S_ALGO_TENSOR request is always honoured.
+    if (f->algo == B2S_ALGO_TENSOR && f->algo_req == B2S_ALGO_AUTO) {
+        const double per_tap = f->kind == B2S_F32_F32 ? 6.9e-14 : 1.15e-13;
+        if ((double)n_out * (double)f->ntaps * per_tap < 10e-6) return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);
+    }
     if (f->algo == B2S_ALGO_TENSOR) return fir_tc_launch(f, d_in, n_in, d_out, n_out, stream);
     if (f->algo == B2S_ALGO_FFT) return fir_fft_launch(f, d_in, n_in, d_out, n_out, stream);
     return fir_direct_launch(f, d_in, n_in, d_out, n_out, stream);
