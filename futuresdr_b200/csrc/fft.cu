@@ -15,6 +15,7 @@
 // multiply on the store; the inverse transform is conj(FFT(conj(x))) (conjugations are free on
 // load/store).  Twiddles come from a table W_N[k] evaluated in f64 on the host.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "fft_common.cuh"
@@ -118,10 +119,9 @@ constexpr int kFftThreads = 256;
 // (<= 4096: three CTAs per SM as before -- naming a minimum of 1 let ptxas take 111 registers and cost 15 % at 4096.)
 template <int LOG2N> struct FftCfg { static constexpr int THREADS = LOG2N >= 14 ? 512 : 256, MINB = LOG2N >= 14 ? 1 : (LOG2N == 13 ? 2 : 3); };
 
-template <int LOG2N>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) fft_kernel(const FftArgs a) {
+template <int LOG2N, int TH, int MINB>
+__global__ void __launch_bounds__(TH, MINB) fft_kernel(const FftArgs a) {
     constexpr int N = 1 << LOG2N;
-    constexpr int TH = FftCfg<LOG2N>::THREADS;
     using PL = Plan<LOG2N>;
     constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > TH) ? TH : N / 16);                     // threads per transform
     constexpr int FPB = TH / T;                                                             // transforms per CTA
@@ -153,14 +153,13 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
     }
 }
 
-template <int LOG2N>
-int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
+template <int LOG2N, int TH, int MINB>
+int32_t launch_fft_cfg(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
-    constexpr int TH = FftCfg<LOG2N>::THREADS;
     constexpr int T = (N / 16 < 1) ? 1 : ((N / 16 > TH) ? TH : N / 16);
     constexpr int FPB = TH / T;
     constexpr size_t smem = (size_t)FPB * (N + N / 16) * sizeof(float2);
-    auto kern = fft_kernel<LOG2N>;
+    auto kern = fft_kernel<LOG2N, TH, MINB>;
     if (smem > 48 * 1024) {
         static PerDeviceOnce optin;              // per template instantiation, per device
         if (optin.need(p->ctx->device)) {
@@ -172,6 +171,24 @@ int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
     kern<<<grid, TH, smem, stream>>>(a);
     B2S_CHECK_LAUNCH(p->ctx);
     return B2S_OK;
+}
+
+template <int LOG2N>
+int32_t launch_fft(b2s_fft *p, const FftArgs &a, cudaStream_t stream) {
+    if constexpr (LOG2N == 14) {
+        // one transform = one CTA = one SM (139 KiB of shared memory): 1024 threads run ONE butterfly each per pass at
+        // 64 registers (32 B of spills) and give the SM 32 warps to hide latency with; 512 threads (two butterflies,
+        // 128 registers) is the A/B alternative (B2S_FFT16K_THREADS=512)
+        static const int th = [] { const char *e = getenv("B2S_FFT16K_THREADS"); return e ? atoi(e) : 1024; }();
+        if (th == 512) return launch_fft_cfg<14, 512, 1>(p, a, stream);
+        return launch_fft_cfg<14, 1024, 1>(p, a, stream);
+    } else if constexpr (LOG2N == 13) {
+        static const int th = [] { const char *e = getenv("B2S_FFT8K_THREADS"); return e ? atoi(e) : 256; }();
+        if (th == 512) return launch_fft_cfg<13, 512, 2>(p, a, stream);      // A/B: one butterfly per thread and pass
+        return launch_fft_cfg<13, 256, 2>(p, a, stream);
+    } else {
+        return launch_fft_cfg<LOG2N, FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB>(p, a, stream);
+    }
 }
 
 
