@@ -59,6 +59,7 @@ SIGNATURES = {
     "b2s_pfbarb_plan_c32": (_i32, [_vp, _f32p, _sz, _sz, _f32, _vpp]),
     "b2s_pfbarb_destroy": (None, [_vp]),
     "b2s_pfbarb_reset": (_i32, [_vp]),
+    "b2s_pfbarb_period": (_i32, [_f32, _sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b2s_pfbarb_exec": (_i32, [_vp, _vp, _sz, _vp, _sz, _szp, _szp, _i32p]),
     "b2s_fft_plan_c32": (_i32, [_vp, _sz, _i32, _i32, _i32, _f32, _vpp]),
     "b2s_fft_destroy": (None, [_vp]),

@@ -336,6 +336,18 @@ uint64_t outputs_before(const b2s_pfbarb *p, uint64_t c) {
 
 extern "C" {
 
+// Host-only: the period of the timing recurrence (what the plan's table covers).  No device needed.
+int32_t b2s_pfbarb_period(float rate, size_t num_filters, uint64_t *period_items, uint64_t *outputs_per_period) {
+    if (!(rate > 0.f) || num_filters == 0 || !period_items || !outputs_per_period)
+        return b2s_fail(nullptr, B2S_EINVAL, "b2s_pfbarb_period: bad argument");
+    b2s_pfbarb tmp;
+    tmp.num_filters = num_filters; tmp.rate = rate; tmp.delay = 1.0f / rate;
+    const bool ok = build_periodic_schedule(&tmp);
+    *period_items = ok ? tmp.lambda : 0;
+    *outputs_per_period = ok ? tmp.out_per_period : 0;
+    return B2S_OK;
+}
+
 int32_t b2s_pfbarb_plan_c32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_t num_filters, float rate,
                             b2s_pfbarb **out) {
     if (!ctx || !out || !taps) return b2s_fail(ctx, B2S_EINVAL, "b2s_pfbarb_plan_c32: NULL argument");

@@ -167,6 +167,10 @@ int32_t b2s_pfbarb_plan_c32(b2s_ctx *ctx, const float *taps, size_t ntaps, size_
                             float rate, b2s_pfbarb **out);
 void    b2s_pfbarb_destroy(b2s_pfbarb *p);
 int32_t b2s_pfbarb_reset(b2s_pfbarb *p);
+/* Host-only diagnostic: the timing recurrence (update_timing_state :130-140, `tau -= 1.0` :184-186) is periodic; this
+ * returns the period in input items and the outputs it produces (0, 0 when no cycle shorter than 2^25 items starts at
+ * tau = 0 -- such plans replay the recurrence on the host per call).  Needs no device. */
+int32_t b2s_pfbarb_period(float rate, size_t num_filters, uint64_t *period_items, uint64_t *outputs_per_period);
 int32_t b2s_pfbarb_exec(b2s_pfbarb *p, const void *d_in, size_t n_in, void *d_out, size_t n_out_cap,
                         size_t *consumed, size_t *produced, int32_t *call_again);
 

@@ -259,3 +259,28 @@ def test_synthesizer_oracle_vs_python_transcription(rng):
         assert (c, p) == (consumed, produced)
         if want:
             assert np.max(np.abs(out - np.asarray(want))) <= 1e-4 * (np.max(np.abs(taps)) * T * N * np.max(np.abs(x)))
+
+
+def test_pfbarb_timing_recurrence_is_periodic_and_the_period_matches_the_oracle():
+    """The device PfbArbResampler indexes a table of ONE period of the f32 timing recurrence instead of replaying it
+    per call.  The period finder is host code of the product library (b2s_pfbarb_period, no GPU needed): over exactly
+    one period the oracle state machine must produce exactly `outputs_per_period` outputs, wherever the period starts."""
+    import ctypes as C
+    import oracle as orc
+    from futuresdr_b200._lib import lib
+    rng = np.random.default_rng(3)
+    for rate, nfilt in ((0.768, 32), (2.3, 32), (1.5, 4), (0.9, 16), (1.0, 8)):
+        lam, outs = C.c_uint64(0), C.c_uint64(0)
+        assert lib.b2s_pfbarb_period(C.c_float(rate), nfilt, C.byref(lam), C.byref(outs)) == 0
+        lam, outs = lam.value, outs.value
+        assert lam > 0 and outs > 0
+        # outputs per input over a period = the rate, to the precision of the f32 reciprocal
+        assert abs(outs / lam - rate) / rate < 1e-6
+        T = 4
+        taps = np.ones(nfilt * T, np.float32)
+        n0 = T + 1000                                  # window fill + an arbitrary offset into the cycle
+        reps = max(1, 3_000_000 // lam)                # short periods: count over many of them
+        x = (rng.standard_normal(n0 + reps * lam) + 0j).astype(np.complex64)
+        a = orc.PfbArb(rate, taps, nfilt).run(x[:n0], out_cap_per_call=1 << 24).size
+        b = orc.PfbArb(rate, taps, nfilt).run(x, out_cap_per_call=1 << 24).size
+        assert b - a == reps * outs, (rate, lam, outs, b - a)
