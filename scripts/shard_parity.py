@@ -19,9 +19,11 @@ import futuresdr_b200 as fb  # noqa: E402
 from futuresdr_b200.shard import ShardedFir  # noqa: E402
 import oracle as orc  # noqa: E402
 
-CASES = (  # ntaps, decim, S, steps
-    (256, 1, 1 << 16, 4), (1024, 1, 1 << 15, 3), (52, 4, 1 << 14, 4), (64, 1, 8192, 5), (129, 1, 1 << 15, 3),
-    (33, 2, 1 << 13, 3), (257, 1, 1 << 15, 3),
+CASES = (  # ntaps, decim, S, steps, sample dtype
+    (256, 1, 1 << 16, 4, np.complex64), (1024, 1, 1 << 15, 3, np.complex64), (52, 4, 1 << 14, 4, np.complex64),
+    (64, 1, 8192, 5, np.complex64), (129, 1, 1 << 15, 3, np.complex64), (33, 2, 1 << 13, 3, np.complex64),
+    (257, 1, 1 << 15, 3, np.complex64),
+    (64, 1, 1 << 14, 4, np.float32), (100, 4, 1 << 14, 3, np.float32), (255, 1, 1 << 15, 3, np.float32),
 )
 
 
@@ -33,17 +35,21 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ok, report = True, []
     for exchange in ("peer", "nccl"):
-        for ntaps, decim, S, steps in CASES:
+        for ntaps, decim, S, steps, sdt in CASES:
             rng = np.random.default_rng(123)
             total = world * S * steps
-            x = (rng.standard_normal(total) + 1j * rng.standard_normal(total)).astype(np.complex64)
+            if sdt == np.complex64:
+                x = (rng.standard_normal(total) + 1j * rng.standard_normal(total)).astype(np.complex64)
+            else:
+                x = rng.standard_normal(total).astype(np.float32)
+            tdt = torch.complex64 if sdt == np.complex64 else torch.float32
             taps = rng.uniform(-1, 1, ntaps).astype(np.float32)
-            sh = ShardedFir(taps, S, np.complex64, decim=decim, device=dev, exchange=exchange)
+            sh = ShardedFir(taps, S, sdt, decim=decim, device=dev, exchange=exchange)
             outs = []
             for t in range(steps):
                 lo = (t * world + rank) * S
                 sh.chunk.copy_(torch.from_numpy(x[lo:lo + S]).to(dev))
-                out = torch.zeros(S // decim, dtype=torch.complex64, device=dev)
+                out = torch.zeros(S // decim, dtype=tdt, device=dev)
                 c, p, st = sh.step(out)
                 # no synchronisation between steps in peer mode: ordering is the device flags' job
                 outs.append((t * world + rank, out, p))
@@ -61,7 +67,7 @@ def main():
                 err = float(np.max(np.abs(got - ref))) if got.size == ref.size else float("inf")
                 good = got.size == ref.size and err <= tol
                 ok = ok and good
-                row = {"world": world, "exchange": exchange, "ntaps": ntaps, "decim": decim, "chunk": S, "steps": steps,
+                row = {"world": world, "exchange": exchange, "samples": np.dtype(sdt).name, "ntaps": ntaps, "decim": decim, "chunk": S, "steps": steps,
                        "algo": int(sh._filter.algo), "n_out": int(got.size), "n_ref": int(ref.size), "max_err": err,
                        "tol": tol, "ok": bool(good)}
                 report.append(row)
