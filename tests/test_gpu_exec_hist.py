@@ -131,19 +131,20 @@ def test_exec_hist_flags_and_timeout():
     fir.ctx.sync()      # status word was cleared: the context stays usable
 
 
-@pytest.mark.parametrize("ntaps,decim,S", [(256, 1, 1 << 16), (52, 4, 1 << 14), (1024, 1, 1 << 15), (64, 1, 8192)])
-def test_peer_exchange_single_rank_stream(ntaps, decim, S):
+@pytest.mark.parametrize("dtype", [np.complex64, np.float32])
+@pytest.mark.parametrize("ntaps,decim,S", [(256, 1, 1 << 16), (52, 4, 1 << 14), (1024, 1, 1 << 15), (64, 1, 8192), (255, 1, 1 << 15)])
+def test_peer_exchange_single_rank_stream(ntaps, decim, S, dtype):
     """world == 1 through the ring: chunk t's history is the tail of the previous SLOT (no copy on the tensor path);
     the concatenated outputs equal the single-stream oracle result, first chunk shorter by ntaps-1."""
     from futuresdr_b200.shard import ShardedFir
     steps = 5
     taps = np.random.default_rng(6).uniform(-1, 1, ntaps).astype(np.float32)
-    x = _noise(S * steps, np.complex64, 31)
-    sh = ShardedFir(taps, S, np.complex64, decim=decim, exchange="peer")
+    x = _noise(S * steps, dtype, 31)
+    sh = ShardedFir(taps, S, dtype, decim=decim, exchange="peer")
     got = []
     for t in range(steps):
         sh.chunk.copy_(torch.from_numpy(x[t * S:(t + 1) * S]).cuda())
-        out = torch.zeros(S // decim, dtype=torch.complex64, device="cuda")
+        out = torch.zeros(S // decim, dtype=torch.complex64 if np.dtype(dtype) == np.complex64 else torch.float32, device="cuda")
         c, p, st = sh.step(out)
         got.append((out, p))
     sh.ctx.sync()
