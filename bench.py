@@ -986,7 +986,7 @@ def run_ours(args):
                     "host_copy_ceiling": ceiling},
             "gpu_launches": int(launches),
             "parity": {"headline": "pinned: FirFilter is checked against the reference's known-answer vectors (fir.rs:283-365) through the oracle and the C ABI; tolerance 1e-5 * ||taps||_1 * max|x|",
-                       "secondary": "configs[0], [4]: pinned (FIR).  configs[2] (PfbArbResampler, demod closure), configs[3] (Fft = rustfft, un-vendored), spectrum pipe, ring x12: parity UNPINNED -- the reference holds no value test; the oracle is a restatement of the cited lines"},
+                       "secondary": "configs[0], [4]: pinned (FIR).  MovingAvg: pinned (tests/moving_avg.rs).  configs[2] (PfbArbResampler, demod closure), configs[3] (Fft = rustfft, un-vendored), the FFT part of the spectrum pipe: parity UNPINNED -- the reference holds no value test; the oracle is a restatement of the cited lines.  Ring x12: the reference's own check (tests/vulkan.rs:73-75) is applied in the run"},
             "clocks": clocks,
             "per_rank": per_rank, "host_enqueue_us_per_step": host_step_us,
             "secondary": secondary,

@@ -208,6 +208,15 @@ int main() {
         auto v = m.output();
         CHECK(v.size() == 8);
         for (size_t i = 0; i < v.size() && i < 8; i++) CHECK(v[i] == (i < 4 ? 1.75f : 5.1875f));
+        {   // the reference's own known answer (tests/moving_avg.rs:7-19): exact f32 equality
+            MovingAvg ref(inst, 3, 0.1f, 3);
+            Mocker mr(ref);
+            mr.input(std::vector<float>{1.f, 2.f, 3.f, 1.f, 2.f, 3.f, 1.f, 2.f, 3.f});
+            mr.init_output(3);
+            mr.run();
+            auto r = mr.output();
+            CHECK(r.size() == 3 && r[0] == 0.271f && r[1] == 0.542f && r[2] == 0.813f);
+        }
         bool threw = false;
         try { MovingAvg bad(inst, 4, 1.5f, 2); } catch (const Error &) { threw = true; }
         CHECK(threw);                                                    // assert!((0.0..=1.0).contains(&decay_factor))

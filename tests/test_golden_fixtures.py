@@ -47,3 +47,34 @@ def test_device_reproduces_reference_vector(case):
     torch.cuda.synchronize()
     assert (c, p, int(st)) == (case["consumed"], case["produced"], case["status"]), case["cite"]
     assert list(map(float, out[:p].cpu().numpy())) == list(map(float, case["output"])), case["cite"]
+
+
+# ---- block-level known answers (tests/moving_avg.rs): MovingAvg is PINNED by the reference's own vectors ------------
+BLOCK_CASES = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_known_answers.json")))["block_cases"]
+
+
+def _f32(vals):
+    return np.asarray([float(v) for v in vals], np.float32)       # "nan" / "inf" strings -> non-finite floats
+
+
+@pytest.mark.parametrize("case", BLOCK_CASES, ids=[c["cite"].split()[-1] for c in BLOCK_CASES])
+def test_oracle_reproduces_reference_block_vector(case):
+    m = orc.MovingAvg(case["width"], case["decay_factor"], case["history_size"])
+    c, p, o = m.work(_f32(case["input"]), case["out_cap"])
+    assert p == len(case["output"])
+    assert np.array_equal(o, np.asarray(case["output"], np.float32)), case["cite"]     # assert_eq! on Vec<f32>
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", BLOCK_CASES, ids=[c["cite"].split()[-1] for c in BLOCK_CASES])
+def test_device_reproduces_reference_block_vector(case):
+    import torch
+    from futuresdr_b200.blocks import Mocker, MovingAvg
+    blk = MovingAvg(case["width"], case["decay_factor"], case["history_size"])
+    m = Mocker(blk)
+    m.input(_f32(case["input"]))
+    m.init_output(case["out_cap"])
+    m.run()
+    torch.cuda.synchronize()
+    got = m.output().cpu().numpy()
+    assert np.array_equal(got, np.asarray(case["output"], np.float32)), case["cite"]
