@@ -239,7 +239,8 @@ int32_t b2s_chan_exec(b2s_chan *c, const void *d_in, size_t n_in, void *d_out, s
 
 /* ---- PfbSynthesizer (≙ src/blocks/pfb/synthesizer.rs:52-144): N-point inverse FFT per
  * input vector + polyphase FIR bank, N outputs per vector.  d_in is channel-major (stream w starts at
- * d_in + w * in_stride items), n_in = the shortest input slice.  One exec == one Kernel::work call. */
+ * d_in + w * in_stride items), n_in = the shortest input slice.  One exec == one Kernel::work call.
+ * Power-of-two banks up to 256 channels with <= 32 taps per arm run as ONE fused kernel in the steady state. */
 typedef struct b2s_synth b2s_synth;
 int32_t b2s_synth_plan_c32(b2s_ctx *ctx, size_t num_channels, const float *taps, size_t ntaps, b2s_synth **out);
 void    b2s_synth_destroy(b2s_synth *s);

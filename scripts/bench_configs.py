@@ -114,6 +114,23 @@ def main():
                 ch.work(B.WorkIo())
             sec = timeit(run_ch, iters=5, warm=1)
             report(f"pfb_channelizer_fused_{N}ch_{T}taps", n, 16 * n, sec, extra="FIR bank + IFFT + transposed store in one launch")
+    if want("synth"):
+        for N, T in ((64, 16), (16, 16)):
+            staps = np.resize((orc.kaiser_lowpass(0.4 / N, 0.1 / N, 1e-3)).astype(np.float32), N * T)
+            syn = B.PfbSynthesizer(N, staps)
+            nv = n // N
+            xin = x[:N * nv].view(N, nv)
+            syn.set_inputs(xin[:, :4 * T])                    # window fill
+            syn.output.reserve(8 * T * N)
+            syn.work(B.WorkIo())
+            syn.set_inputs(xin)
+            syn.output.reserve(n + 2 * N)
+
+            def run_syn():
+                syn.in_pos, syn.output.len = 0, 0
+                syn.work(B.WorkIo())
+            sec = timeit(run_syn, iters=5, warm=1)
+            report(f"pfb_synthesizer_{N}ch_{T}taps", n, 16 * n, sec, extra="gather + IFFT + FIR bank")
     if want("f32"):
         # f32 x f32 64 taps (perf/fir config-1 kernel)
         xr = torch.view_as_real(x).reshape(-1)[: 2 * n]
