@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(256) chan_fused_kernel(const float2 *__restric
     const int b = tid % N, run = tid / N;
     int r = (base0 - b) % N; if (r < 0) r += N;              // window b receives samples == r (mod N)
     int arm = (b - base0 - 1) % N; if (arm < 0) arm += N;    // and always meets this arm
-    float tap[TPAD];
+    unsigned long long tap[TPAD];            // (t, t) pairs: one FFMA2 per complex x real MAC (common.cuh cmac2)
 #pragma unroll
-    for (int j = 0; j < TPAD; j++) tap[j] = __ldg(arms_pad + (size_t)j * N + arm);
+    for (int j = 0; j < TPAD; j++) tap[j] = dup2(__ldg(arms_pad + (size_t)j * N + arm));
 
     auto fetch = [&](int tile, float2 *X) {                  // A: the (OB + TPAD - 1) * N samples tile `tile` depends on
         const long long base = (o_first + (long long)tile * OB - (TPAD - 1)) * N;   // rows in front of the call meet zero taps
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) chan_fused_kernel(const float2 *__restric
 #pragma unroll
                 for (int u = 0; u < RL; u++) {
                     const int j = u + TPAD - 1 - k;          // output u sees this row as its j-th newest sample
-                    if (j >= 0 && j < TPAD) { acc[u].x = fmaf(x.x, tap[j], acc[u].x); acc[u].y = fmaf(x.y, tap[j], acc[u].y); }
+                    if (j >= 0 && j < TPAD) cmac2(acc[u], x, tap[j]);
                 }
             }
 #pragma unroll

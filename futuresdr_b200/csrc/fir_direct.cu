@@ -80,8 +80,14 @@ template <typename S, typename T, int R>
 __device__ __forceinline__ void mac_chunk(S (&acc)[R], const S (&lo)[R], const S (&hi)[R], const T (&tp)[R]) {
 #pragma unroll
     for (int j = 0; j < R; j++) {
+        if constexpr (sizeof(S) == 8 && sizeof(T) == 4) {          // complex sample x real tap: one FFMA2 per MAC
+            const unsigned long long tt = dup2(tp[j]);
 #pragma unroll
-        for (int r = 0; r < R; r++) mac(acc[r], (r + j < R) ? lo[(r + j) % R] : hi[(r + j) % R], tp[j]);
+            for (int r = 0; r < R; r++) cmac2(acc[r], (r + j < R) ? lo[(r + j) % R] : hi[(r + j) % R], tt);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) mac(acc[r], (r + j < R) ? lo[(r + j) % R] : hi[(r + j) % R], tp[j]);
+        }
     }
 }
 // one phase row: nchunk chunks of R taps against the thread's sliding window starting at segment seg0
@@ -316,7 +322,7 @@ __global__ void fir_naive_kernel(const S *__restrict__ in, S *__restrict__ out,
 template <typename S, int R, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *__restrict__ gtab,
-                    int L, int M, int Upad, int pitch /*items per phase row*/, int opitch /*chunks per output row*/,
+                    int L, int M, int Upad, int pitch /*items per phase row*/, int opitch /*bytes of the output staging*/,
                     long long n_in, long long n_out, int vec_ok) {
     constexpr int EPC = 16 / sizeof(S);
     constexpr int TK = THREADS * R;                 // j's per CTA; the CTA produces L*TK outputs
@@ -325,8 +331,8 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
     const long long j0 = (long long)blockIdx.x * TK;
     const int W = TK + Upad;
     unsigned char *xs = smem;                                                    // [M][pitch] items
-    unsigned char *os = smem + (size_t)M * pitch * sizeof(S);                    // [L][opitch] 16-byte chunks
-    float *gs = reinterpret_cast<float *>(os + (size_t)L * opitch * 16);         // [L][M][Upad]
+    unsigned char *os = smem + (size_t)M * pitch * sizeof(S);                    // THREADS segments of R*L + 1 items (opitch bytes in all)
+    float *gs = reinterpret_cast<float *>(os + (size_t)opitch);                  // [L][M][Upad]
 
     for (int i = tid; i < L * M * Upad; i += THREADS) gs[i] = gtab[i];
 
@@ -396,40 +402,30 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
         for (int q = 0; q < M; q++)
             fir_row<S, float, R>(acc, xs + (size_t)q * pitch * sizeof(S), q & 7, tid, gs + ((size_t)k0 * M + q) * Upad,
                                  nchunk_taps);
-        // row k0 of the output staging: this thread's R consecutive j's, swizzled 16-byte chunks
-        constexpr int CPS = R / EPC;
-        unsigned char *orow = os + (size_t)k0 * opitch * 16;
+        // output staging in FINAL order: this thread's R*L outputs o = L*(R*tid + r) + k0 form one segment of R*L items;
+        // segments are R*L + 1 items apart (odd stride: the lanes of a warp hit distinct banks)
+        S *oseg = reinterpret_cast<S *>(os) + (size_t)tid * (R * L + 1) + k0;
 #pragma unroll
-        for (int jj = 0; jj < CPS; jj++) {
-            float4 v;
-            if constexpr (sizeof(S) == 8) {
-                v = make_float4(acc[2 * jj].x, acc[2 * jj].y, acc[2 * jj + 1].x, acc[2 * jj + 1].y);
-            } else {
-                v = make_float4(*reinterpret_cast<float *>(&acc[4 * jj]), *reinterpret_cast<float *>(&acc[4 * jj + 1]),
-                                *reinterpret_cast<float *>(&acc[4 * jj + 2]), *reinterpret_cast<float *>(&acc[4 * jj + 3]));
-            }
-            *reinterpret_cast<float4 *>(orow + swz(tid * CPS + jj) * 16) = v;
-        }
+        for (int r = 0; r < R; r++) oseg[r * L] = acc[r];
     }
     __syncthreads();
 
-    // ---- interleave the L rows back into output order: o = L*j + k0, contiguous 16-byte vector stores
+    // ---- contiguous 16-byte vector stores; chunk c holds outputs [c*EPC, (c+1)*EPC) of the tile, which sit in ONE
+    //      segment (R*L is a multiple of EPC) at item index p + p / (R*L)
     {
         const long long o0 = j0 * L;
+        const int SEGL = R * L;
         const int nout_chunks = L * TK / EPC;                       // TK is a multiple of EPC
-        int k = (tid * EPC) % L, j = (tid * EPC) / L;
-        const int dk = (THREADS * EPC) % L, dj = (THREADS * EPC) / L;
+        const S *ob = reinterpret_cast<const S *>(os);
+        int seg = (tid * EPC) / SEGL, rem = (tid * EPC) % SEGL;
+        const int dseg = (THREADS * EPC) / SEGL, drem = (THREADS * EPC) % SEGL;
         for (int c = tid; c < nout_chunks; c += THREADS) {
             const long long o = o0 + (long long)c * EPC;
             if (o >= n_out) break;
+            const S *src = ob + c * EPC + seg;
             S items[EPC];
-            int ke = k, je = j;
 #pragma unroll
-            for (int e = 0; e < EPC; e++) {
-                const int chunk = je / EPC, el = je % EPC;
-                items[e] = *reinterpret_cast<const S *>(os + ((size_t)ke * opitch + swz(chunk)) * 16 + el * sizeof(S));
-                if (++ke == L) { ke = 0; je++; }
-            }
+            for (int e = 0; e < EPC; e++) items[e] = src[e];
             if (vec_ok && o + EPC <= n_out) {
                 *reinterpret_cast<float4 *>(out + o) = *reinterpret_cast<float4 *>(items);
             } else {
@@ -437,8 +433,8 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
                 for (int e = 0; e < EPC; e++)
                     if (o + e < n_out) out[o + e] = items[e];
             }
-            k += dk; j += dj;
-            if (k >= L) { k -= L; j += 1; }
+            seg += dseg; rem += drem;
+            if (rem >= SEGL) { rem -= SEGL; seg += 1; }
         }
     }
 }
@@ -522,10 +518,11 @@ int32_t fir_direct_launch(b2s_fir *f, const void *d_in, size_t n_in, void *d_out
 namespace {
 constexpr int kRsSlideThreads = 128;
 constexpr size_t kRsSlideSmemMax = 96 * 1024;        // keep >= 2 CTAs per SM
+size_t resamp_slide_ostage(size_t L, size_t isz) { return round_up((size_t)kRsSlideThreads * (kR * L + 1) * isz, 16); }
 size_t resamp_slide_smem(size_t L, size_t M, size_t Upad, size_t isz) {
     const size_t TK = (size_t)kRsSlideThreads * kR, EPC = 16 / isz;
-    const size_t pitch = round_up(TK + Upad, 8 * EPC), opitch = TK / EPC + 1;
-    return M * pitch * isz + L * opitch * 16 + L * M * Upad * sizeof(float);
+    const size_t pitch = round_up(TK + Upad, 8 * EPC);
+    return M * pitch * isz + resamp_slide_ostage(L, isz) + L * M * Upad * sizeof(float);
 }
 }  // namespace
 
@@ -558,18 +555,26 @@ int32_t resamp_slide_launch(b2s_ctx *ctx, b2s_kind kind, const float *d_gtab, si
     const size_t isz = kind_in_bytes(kind), EPC = 16 / isz;
     const size_t Upad = (size_t)resamp_slide_upad(M, T);
     const size_t TK = (size_t)kRsSlideThreads * kR;
-    const int pitch = (int)round_up(TK + Upad, 8 * EPC), opitch = (int)(TK / EPC + 1);
+    const int pitch = (int)round_up(TK + Upad, 8 * EPC), opitch = (int)resamp_slide_ostage(L, isz);
     const size_t smem = resamp_slide_smem(L, M, Upad, isz);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
     const unsigned grid = (unsigned)ceil_div(n_out, L * TK);
     if (kind == B2S_F32_F32) {
         auto kern = resamp_slide_kernel<float, kR, kRsSlideThreads>;
-        B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
+        static PerDeviceOnce optin;
+        if (optin.need(ctx->device)) {
+            B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
+            optin.done(ctx->device);
+        }
         kern<<<grid, kRsSlideThreads, smem, stream>>>((const float *)d_in, (float *)d_out, d_gtab, (int)L, (int)M, (int)Upad,
                                                       pitch, opitch, (long long)n_in, (long long)n_out, vec_ok);
     } else {
         auto kern = resamp_slide_kernel<float2, kR, kRsSlideThreads>;
-        B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
+        static PerDeviceOnce optin;
+        if (optin.need(ctx->device)) {
+            B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
+            optin.done(ctx->device);
+        }
         kern<<<grid, kRsSlideThreads, smem, stream>>>((const float2 *)d_in, (float2 *)d_out, d_gtab, (int)L, (int)M, (int)Upad,
                                                       pitch, opitch, (long long)n_in, (long long)n_out, vec_ok);
     }

@@ -193,7 +193,11 @@ int32_t launch_spectrum(b2s_spectrum *p, const SpArgs &a, cudaStream_t stream) {
     constexpr int FPB = kSpThreads / T;
     constexpr size_t smem = (size_t)FPB * (N + N / 16 + N) * sizeof(float2);
     auto kern = spectrum_kernel<LOG2N>;
-    if (smem > 48 * 1024) B2S_CUDA(p->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static PerDeviceOnce optin;                  // per template instantiation, per device
+    if (smem > 48 * 1024 && optin.need(p->ctx->device)) {
+        B2S_CUDA(p->ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        optin.done(p->ctx->device);
+    }
     const unsigned grid = (unsigned)ceil_div((size_t)a.groups, (size_t)FPB);
     kern<<<grid, kSpThreads, smem, stream>>>(a);
     B2S_CHECK_LAUNCH(p->ctx);
