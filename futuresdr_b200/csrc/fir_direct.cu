@@ -112,6 +112,40 @@ __device__ __forceinline__ void fir_row(S (&acc)[R], const unsigned char *row, i
     }
 }
 
+// The same phase row against LT tap tables at once (the rational resampler's L polyphase banks, `bank_stride` floats
+// apart): every window segment is loaded ONCE and multiplied into all LT accumulator sets, so the shared-memory
+// traffic per MAC drops by LT (ncu on the one-bank-at-a-time loop: LSU wavefronts and the FMA pipe within 20 % of each other).
+template <typename S, int R, int LT>
+__device__ __forceinline__ void fir_row_banks(S (&acc)[LT][R], const unsigned char *row, int rq, int seg0, const float *g,
+                                              int bank_stride, int nchunk) {
+    S a[R], b[R];
+    float tp[R];
+    load_segment<S, R>(a, row, seg0, rq);
+    int c = 0;
+    for (; c + 1 < nchunk; c += 2) {
+        load_segment<S, R>(b, row, seg0 + c + 1, rq);
+#pragma unroll
+        for (int k = 0; k < LT; k++) {
+            load_taps<float, R>(tp, g + k * bank_stride + c * R);
+            mac_chunk<S, float, R>(acc[k], a, b, tp);
+        }
+        load_segment<S, R>(a, row, seg0 + c + 2, rq);
+#pragma unroll
+        for (int k = 0; k < LT; k++) {
+            load_taps<float, R>(tp, g + k * bank_stride + (c + 1) * R);
+            mac_chunk<S, float, R>(acc[k], b, a, tp);
+        }
+    }
+    if (c < nchunk) {
+        load_segment<S, R>(b, row, seg0 + c + 1, rq);
+#pragma unroll
+        for (int k = 0; k < LT; k++) {
+            load_taps<float, R>(tp, g + k * bank_stride + c * R);
+            mac_chunk<S, float, R>(acc[k], a, b, tp);
+        }
+    }
+}
+
 // Interior-tile staging for D > 1: the tile's D*W items are all inside the input and the base is 16-byte
 // aligned, so whole groups of THREADS*UNR float4 chunks are loaded with no predicates, 32-bit offsets and a
 // running pointer; the ragged end of the tile and edge tiles go through the generic loops in the kernels.
@@ -319,10 +353,12 @@ __global__ void fir_naive_kernel(const S *__restrict__ in, S *__restrict__ out,
 // output reading every sample from shared memory (resamp.cu) this does R*R MACs per R-item segment
 // load instead of 1.6 FMA per LDS.
 // ---------------------------------------------------------------------------------------------
-template <typename S, int R, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// LT = L when it is one of the instantiated interpolation factors (all banks per segment load), else 0 (one bank at a time)
+template <typename S, int R, int THREADS, int LT>
+__global__ void __launch_bounds__(THREADS, LT == 3 ? 5 : 1)        // L = 3: 99 -> 94 registers = a fifth resident CTA, no spills
 resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *__restrict__ gtab,
                     int L, int M, int Upad, int pitch /*items per phase row*/, int opitch /*bytes of the output staging*/,
+                    int os_off /*byte offset of the output staging: 0 = it reuses the input rows*/,
                     long long n_in, long long n_out, int vec_ok) {
     constexpr int EPC = 16 / sizeof(S);
     constexpr int TK = THREADS * R;                 // j's per CTA; the CTA produces L*TK outputs
@@ -331,8 +367,9 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
     const long long j0 = (long long)blockIdx.x * TK;
     const int W = TK + Upad;
     unsigned char *xs = smem;                                                    // [M][pitch] items
-    unsigned char *os = smem + (size_t)M * pitch * sizeof(S);                    // THREADS segments of R*L + 1 items (opitch bytes in all)
-    float *gs = reinterpret_cast<float *>(os + (size_t)opitch);                  // [L][M][Upad]
+    unsigned char *os = smem + os_off;                                           // THREADS segments of R*L + 1 items (opitch bytes in all)
+    const size_t xs_bytes = (size_t)M * pitch * sizeof(S);
+    float *gs = reinterpret_cast<float *>(smem + (os_off ? xs_bytes + opitch : (xs_bytes > (size_t)opitch ? xs_bytes : (size_t)opitch)));   // [L][M][Upad]
 
     for (int i = tid; i < L * M * Upad; i += THREADS) gs[i] = gtab[i];
 
@@ -395,18 +432,34 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
 
     // ---- one sliding-window pass per k0
     const int nchunk_taps = Upad / R;
-    for (int k0 = 0; k0 < L; k0++) {
-        S acc[R];
+    if constexpr (LT > 0) {
+        S acc[LT][R];
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = zero_of<S>();
+        for (int k = 0; k < LT; k++)
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[k][r] = zero_of<S>();
         for (int q = 0; q < M; q++)
-            fir_row<S, float, R>(acc, xs + (size_t)q * pitch * sizeof(S), q & 7, tid, gs + ((size_t)k0 * M + q) * Upad,
-                                 nchunk_taps);
-        // output staging in FINAL order: this thread's R*L outputs o = L*(R*tid + r) + k0 form one segment of R*L items;
-        // segments are R*L + 1 items apart (odd stride: the lanes of a warp hit distinct banks)
-        S *oseg = reinterpret_cast<S *>(os) + (size_t)tid * (R * L + 1) + k0;
+            fir_row_banks<S, R, LT>(acc, xs + (size_t)q * pitch * sizeof(S), q & 7, tid, gs + (size_t)q * Upad, M * Upad, nchunk_taps);
+        if (os_off == 0) __syncthreads();                // the staging reuses the input rows: everyone is done reading them
+        S *oseg = reinterpret_cast<S *>(os) + (size_t)tid * (R * LT + 1);
 #pragma unroll
-        for (int r = 0; r < R; r++) oseg[r * L] = acc[r];
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int k = 0; k < LT; k++) oseg[r * LT + k] = acc[k][r];
+    } else {
+        for (int k0 = 0; k0 < L; k0++) {
+            S acc[R];
+    #pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = zero_of<S>();
+            for (int q = 0; q < M; q++)
+                fir_row<S, float, R>(acc, xs + (size_t)q * pitch * sizeof(S), q & 7, tid, gs + ((size_t)k0 * M + q) * Upad,
+                                     nchunk_taps);
+            // output staging in FINAL order: this thread's R*L outputs o = L*(R*tid + r) + k0 form one segment of R*L items;
+            // segments are R*L + 1 items apart (odd stride: the lanes of a warp hit distinct banks)
+            S *oseg = reinterpret_cast<S *>(os) + (size_t)tid * (R * L + 1) + k0;
+    #pragma unroll
+            for (int r = 0; r < R; r++) oseg[r * L] = acc[r];
+        }
     }
     __syncthreads();
 
@@ -519,10 +572,16 @@ namespace {
 constexpr int kRsSlideThreads = 128;
 constexpr size_t kRsSlideSmemMax = 96 * 1024;        // keep >= 2 CTAs per SM
 size_t resamp_slide_ostage(size_t L, size_t isz) { return round_up((size_t)kRsSlideThreads * (kR * L + 1) * isz, 16); }
+bool resamp_slide_banks(size_t L) {                    // L with an all-banks-per-segment instantiation (resamp_slide_launch)
+    static const bool off = getenv("B2S_RESAMP_NO_BANKS") != nullptr;         // A/B switch: one bank at a time
+    return !off && L >= 2 && L <= 4;
+}
 size_t resamp_slide_smem(size_t L, size_t M, size_t Upad, size_t isz) {
     const size_t TK = (size_t)kRsSlideThreads * kR, EPC = 16 / isz;
     const size_t pitch = round_up(TK + Upad, 8 * EPC);
-    return M * pitch * isz + resamp_slide_ostage(L, isz) + L * M * Upad * sizeof(float);
+    const size_t xs = M * pitch * isz, os = resamp_slide_ostage(L, isz);
+    // the all-banks kernel writes its outputs after the last read of the input rows, so the two stagings share memory
+    return (resamp_slide_banks(L) ? std::max(xs, os) : xs + os) + L * M * Upad * sizeof(float);
 }
 }  // namespace
 
@@ -557,27 +616,27 @@ int32_t resamp_slide_launch(b2s_ctx *ctx, b2s_kind kind, const float *d_gtab, si
     const size_t TK = (size_t)kRsSlideThreads * kR;
     const int pitch = (int)round_up(TK + Upad, 8 * EPC), opitch = (int)resamp_slide_ostage(L, isz);
     const size_t smem = resamp_slide_smem(L, M, Upad, isz);
+    const int os_off = resamp_slide_banks(L) ? 0 : (int)((size_t)M * pitch * isz);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
     const unsigned grid = (unsigned)ceil_div(n_out, L * TK);
+#define RS_SLIDE(S, LT)                                                                                                    \
+    do {                                                                                                                   \
+        auto kern = resamp_slide_kernel<S, kR, kRsSlideThreads, LT>;                                                       \
+        static PerDeviceOnce optin;                                                                                        \
+        if (optin.need(ctx->device)) {                                                                                     \
+            B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));  \
+            optin.done(ctx->device);                                                                                       \
+        }                                                                                                                  \
+        kern<<<grid, kRsSlideThreads, smem, stream>>>((const S *)d_in, (S *)d_out, d_gtab, (int)L, (int)M, (int)Upad,      \
+                                                      pitch, opitch, os_off, (long long)n_in, (long long)n_out, vec_ok);   \
+    } while (0)
+    const size_t lt = resamp_slide_banks(L) ? L : 0;
     if (kind == B2S_F32_F32) {
-        auto kern = resamp_slide_kernel<float, kR, kRsSlideThreads>;
-        static PerDeviceOnce optin;
-        if (optin.need(ctx->device)) {
-            B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
-            optin.done(ctx->device);
-        }
-        kern<<<grid, kRsSlideThreads, smem, stream>>>((const float *)d_in, (float *)d_out, d_gtab, (int)L, (int)M, (int)Upad,
-                                                      pitch, opitch, (long long)n_in, (long long)n_out, vec_ok);
+        if (lt == 2) RS_SLIDE(float, 2); else if (lt == 3) RS_SLIDE(float, 3); else if (lt == 4) RS_SLIDE(float, 4); else RS_SLIDE(float, 0);
     } else {
-        auto kern = resamp_slide_kernel<float2, kR, kRsSlideThreads>;
-        static PerDeviceOnce optin;
-        if (optin.need(ctx->device)) {
-            B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSlideSmemMax));
-            optin.done(ctx->device);
-        }
-        kern<<<grid, kRsSlideThreads, smem, stream>>>((const float2 *)d_in, (float2 *)d_out, d_gtab, (int)L, (int)M, (int)Upad,
-                                                      pitch, opitch, (long long)n_in, (long long)n_out, vec_ok);
+        if (lt == 2) RS_SLIDE(float2, 2); else if (lt == 3) RS_SLIDE(float2, 3); else if (lt == 4) RS_SLIDE(float2, 4); else RS_SLIDE(float2, 0);
     }
+#undef RS_SLIDE
     B2S_CHECK_LAUNCH(ctx);
     return B2S_OK;
 }
