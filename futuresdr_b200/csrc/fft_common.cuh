@@ -105,9 +105,32 @@ template <> struct Plan<14> { static constexpr int P = 4, R0 = 16, R1 = 16, R2 =
 
 // One Stockham pass: loads through `load`, optional CTA barrier (in-place passes), twiddles, DFT,
 // stores through `store`, CTA barrier.
-template <int N, int R, int NS, int T, typename LoadF, typename StoreF>
-__device__ __forceinline__ void ss_pass(LoadF load, StoreF store, const float2 *__restrict__ tw, int t,
-                                        bool sync_between) {
+// The pass's base twiddle of butterfly j: a table lookup, or (TwPre) a value the caller fetched ahead of time -- with
+// one butterfly per thread the index depends on the thread alone, so a kernel that runs the same plan repeatedly loads
+// it once instead of waiting for a global load after every barrier.
+struct TwTable {
+    const float2 *__restrict__ tw;
+    template <int N, int R, int NS> __device__ __forceinline__ float2 get(int j, int) const {
+        return __ldg(tw + (j & (NS - 1)) * (N / (NS * R)));
+    }
+};
+struct TwPre {
+    float2 w;
+    template <int N, int R, int NS> __device__ __forceinline__ float2 get(int, int) const { return w; }
+};
+// Base twiddles of one whole pass (ITER butterflies per thread), fetched before the PREVIOUS pass runs.
+template <int N, int R, int NS, int T> struct TwAhead {
+    static constexpr int ITER = (N / R) / T > 0 ? (N / R) / T : 1;
+    float2 w[ITER];
+    __device__ __forceinline__ void fetch(const float2 *__restrict__ tw, int t) {
+#pragma unroll
+        for (int it = 0; it < ITER; it++) w[it] = __ldg(tw + ((t + it * T) & (NS - 1)) * (N / (NS * R)));
+    }
+    template <int N_, int R_, int NS_> __device__ __forceinline__ float2 get(int, int it) const { return w[it]; }
+};
+
+template <int N, int R, int NS, int T, typename LoadF, typename StoreF, typename TwF>
+__device__ __forceinline__ void ss_pass_tw(LoadF load, StoreF store, TwF twf, int t, bool sync_between) {
     constexpr int NB = N / R, ITER = NB / T;
     static_assert(NB % T == 0 || NB < T, "butterflies must tile the threads");
     float2 v[ITER][R];
@@ -121,17 +144,19 @@ __device__ __forceinline__ void ss_pass(LoadF load, StoreF store, const float2 *
 #pragma unroll
     for (int it = 0; it < ITER; it++) {
         const int j = t + it * T;
-        if constexpr (NS > 1) {
-            const int k = j & (NS - 1);
-            constexpr int STEP = N / (NS * R);
-            apply_twiddles<R>(v[it], __ldg(tw + k * STEP));
-        }
+        if constexpr (NS > 1) apply_twiddles<R>(v[it], twf.template get<N, R, NS>(j, it));
         Dft<R>::run(v[it]);
         const int j0 = (j / NS) * NS * R + (j & (NS - 1));
 #pragma unroll
         for (int r = 0; r < R; r++) store(j0 + r * NS, v[it][r]);
     }
     __syncthreads();
+}
+
+template <int N, int R, int NS, int T, typename LoadF, typename StoreF>
+__device__ __forceinline__ void ss_pass(LoadF load, StoreF store, const float2 *__restrict__ tw, int t,
+                                        bool sync_between) {
+    ss_pass_tw<N, R, NS, T>(load, store, TwTable{tw}, t, sync_between);
 }
 
 
@@ -145,20 +170,27 @@ __device__ __forceinline__ void fft_passes(LoadF first_load, StoreF last_store, 
     using PL = Plan<LOG2N>;
     auto ld_sm = [&](int idx) { return sm[pad(idx)]; };
     auto st_sm = [&](int idx, float2 v) { sm[pad(idx)] = v; };
+    // every pass's base twiddles are fetched one pass ahead: the load is in flight across the barrier
     if constexpr (PL::P == 1) {
         ss_pass<N, PL::R0, 1, T>(first_load, last_store, tw, t, first_reads_smem);
     } else if constexpr (PL::P == 2) {
+        TwAhead<N, PL::R1, PL::R0, T> w1; w1.fetch(tw, t);
         ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, first_reads_smem);
-        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, last_store, tw, t, true);
+        ss_pass_tw<N, PL::R1, PL::R0, T>(ld_sm, last_store, w1, t, true);
     } else if constexpr (PL::P == 3) {
+        TwAhead<N, PL::R1, PL::R0, T> w1; w1.fetch(tw, t);
         ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, first_reads_smem);
-        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
-        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, last_store, tw, t, true);
+        TwAhead<N, PL::R2, PL::R0 * PL::R1, T> w2; w2.fetch(tw, t);
+        ss_pass_tw<N, PL::R1, PL::R0, T>(ld_sm, st_sm, w1, t, true);
+        ss_pass_tw<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, last_store, w2, t, true);
     } else {
+        TwAhead<N, PL::R1, PL::R0, T> w1; w1.fetch(tw, t);
         ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, first_reads_smem);
-        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
-        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, st_sm, tw, t, true);
-        ss_pass<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T>(ld_sm, last_store, tw, t, true);
+        TwAhead<N, PL::R2, PL::R0 * PL::R1, T> w2; w2.fetch(tw, t);
+        ss_pass_tw<N, PL::R1, PL::R0, T>(ld_sm, st_sm, w1, t, true);
+        TwAhead<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T> w3; w3.fetch(tw, t);
+        ss_pass_tw<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, st_sm, w2, t, true);
+        ss_pass_tw<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T>(ld_sm, last_store, w3, t, true);
     }
 }
 
@@ -172,17 +204,21 @@ __device__ __forceinline__ void fft_passes_hook(LoadF first_load, HookF after_fi
     static_assert(PL::P >= 2, "fft_passes_hook needs a multi-pass plan");
     auto ld_sm = [&](int idx) { return sm[pad(idx)]; };
     auto st_sm = [&](int idx, float2 v) { sm[pad(idx)] = v; };
+    TwAhead<N, PL::R1, PL::R0, T> w1; w1.fetch(tw, t);
     ss_pass<N, PL::R0, 1, T>(first_load, st_sm, tw, t, false);
     after_first();
     if constexpr (PL::P == 2) {
-        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, last_store, tw, t, true);
+        ss_pass_tw<N, PL::R1, PL::R0, T>(ld_sm, last_store, w1, t, true);
     } else if constexpr (PL::P == 3) {
-        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
-        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, last_store, tw, t, true);
+        TwAhead<N, PL::R2, PL::R0 * PL::R1, T> w2; w2.fetch(tw, t);
+        ss_pass_tw<N, PL::R1, PL::R0, T>(ld_sm, st_sm, w1, t, true);
+        ss_pass_tw<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, last_store, w2, t, true);
     } else {
-        ss_pass<N, PL::R1, PL::R0, T>(ld_sm, st_sm, tw, t, true);
-        ss_pass<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, st_sm, tw, t, true);
-        ss_pass<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T>(ld_sm, last_store, tw, t, true);
+        TwAhead<N, PL::R2, PL::R0 * PL::R1, T> w2; w2.fetch(tw, t);
+        ss_pass_tw<N, PL::R1, PL::R0, T>(ld_sm, st_sm, w1, t, true);
+        TwAhead<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T> w3; w3.fetch(tw, t);
+        ss_pass_tw<N, PL::R2, PL::R0 * PL::R1, T>(ld_sm, st_sm, w2, t, true);
+        ss_pass_tw<N, PL::R3, PL::R0 * PL::R1 * PL::R2, T>(ld_sm, last_store, w3, t, true);
     }
 }
 

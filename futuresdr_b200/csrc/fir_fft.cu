@@ -47,22 +47,34 @@ __global__ void __launch_bounds__(kFfThreads, MINB) fir_fft_kernel(const FftFirA
 
     auto ld_sm = [&](int idx) { return sm[pad(idx)]; };
     auto st_sm = [&](int idx, float2 v) { sm[pad(idx)] = v; };
+    // one butterfly per thread and pass: the base twiddle of a pass depends on the thread alone, so it is fetched one
+    // pass AHEAD (the load is in flight across the barrier instead of being waited for right after it)
+    static_assert(N / 16 == T, "one radix-16 butterfly per thread");
+    const float2 *tw2p = a.tw + (t & 15) * 16, *tw3p = a.tw + t;
+    float2 w = __ldg(tw2p);
     // forward: 16 x 16 x 16
     ss_pass<N, 16, 1, T>([&](int idx) { return idx < avail ? __ldg(in + idx) : make_float2(0.f, 0.f); }, st_sm, a.tw, t, false);
-    ss_pass<N, 16, 16, T>(ld_sm, st_sm, a.tw, t, true);
-    ss_pass<N, 16, 256, T>(ld_sm, st_sm, a.tw, t, true);
+    TwPre twa{w};
+    w = __ldg(tw3p);
+    ss_pass_tw<N, 16, 16, T>(ld_sm, st_sm, twa, t, true);
+    TwPre twb{w};
+    ss_pass_tw<N, 16, 256, T>(ld_sm, st_sm, twb, t, true);
     // inverse = conj(FFT(conj(X . H))): spectrum product + conjugation fused into the first load
+    w = __ldg(tw2p);
     ss_pass<N, 16, 1, T>([&](int idx) {
         const float2 y = cmul(sm[pad(idx)], __ldg(a.H + idx));
         return make_float2(y.x, -y.y);
     }, st_sm, a.tw, t, true);
-    ss_pass<N, 16, 16, T>(ld_sm, st_sm, a.tw, t, true);
+    TwPre twc{w};
+    w = __ldg(tw3p);
+    ss_pass_tw<N, 16, 16, T>(ld_sm, st_sm, twc, t, true);
+    const TwPre tw3{w};
     const long long room = a.n_out - s;
     float2 *out = a.out + s;
     const int V = a.V;
-    ss_pass<N, 16, 256, T>(ld_sm, [&](int idx, float2 v) {
+    ss_pass_tw<N, 16, 256, T>(ld_sm, [&](int idx, float2 v) {
         if (idx < V && idx < room) out[idx] = make_float2(v.x, -v.y);
-    }, a.tw, t, true);
+    }, tw3, t, true);
 }
 
 }  // namespace
