@@ -160,9 +160,14 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
     const long long s_hi = pfb_sub_start(P, sb1 - 1).s_end;
     // arm pairs in shared memory with an ODD row stride: the threads of a warp read different arms at the same tap
     // index, and with a stride of 16 all 32 of them hit two banks (ncu: 176 M bank conflicts, 16 % issue utilisation)
+    // In shared memory the table is PLANAR (one float row per arm, arm b+1 is the second row a thread reads) with an odd
+    // row stride: a 4-byte access has 32 banks for the 32 lanes, so any set of arms is conflict-free at a given tap index
+    // -- the 8-byte pair rows had 16 bank pairs for 32 arms and every load took two passes (ncu, profiles/r2_pfbarb.txt:
+    // 6.46 M wavefronts where 3.24 M are ideal, the LSU pipe 84 % busy).
     const int TS = P.arms_in_smem ? (T | 1) : T;
+    float *s_tap = reinterpret_cast<float *>(s_arms);
     if (P.arms_in_smem)
-        for (int j = threadIdx.x; j < N * T; j += kPaThreads) s_arms[(j / T) * TS + (j % T)] = P.arms[j];
+        for (int j = threadIdx.x; j < N * T; j += kPaThreads) s_tap[(j / T) * TS + (j % T)] = P.arms[j].x;
     if (P.tile_in_smem) {
         // the outputs of sample s read [hist | in][s+1 .. s+T] (Boundary: [s .. s+T-1] as well), s in [s_lo, s_hi):
         // items s_lo .. s_hi+T-1.  (One more would read in[n_in]: compute-sanitizer caught exactly that.)
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
 
     // ---- phase 2: evaluate the outputs.  y0 = arm b0, y1 = arm b0+1 on the same window (Interpolate), or arm N-1 on the
     // previous window and arm 0 on the current one (Boundary): per tap ONE 8-byte sample load and ONE 8-byte tap-pair load
-    const float2 *A = P.arms_in_smem ? s_arms : P.arms;
+    const float2 *A = P.arms;                                    // pair rows in global memory (tables too large for smem)
     const uint32_t cnt = (uint32_t)(o_end - o_first);
     for (uint32_t o = threadIdx.x; o < cnt; o += kPaThreads) {
         const uint32_t w = d_s1[o];
@@ -216,9 +221,29 @@ __global__ void __launch_bounds__(kPaThreads) pfb_kernel(const PaParams P) {
         const int s1 = (int)(w & 0x7fffffffu);                   // relative to s_lo
         const uint32_t b0 = d_b0[o];
         const float mu = d_mu[o];
-        const float2 *pr = A + (size_t)b0 * TS;
+        const float2 *pr = A + (size_t)b0 * T;
         float2 y0 = make_float2(0.f, 0.f), y1 = make_float2(0.f, 0.f);
-        if (P.tile_in_smem) {
+        if (P.tile_in_smem && P.arms_in_smem) {
+            const float *t0 = s_tap + b0 * TS, *t1 = s_tap + (b0 + 1 == (uint32_t)N ? 0u : b0 + 1) * TS;
+            const float2 *xb = s_x + s1;
+            if (!boundary) {
+#pragma unroll 4
+                for (int j = 0; j < T; j++) {
+                    const float2 v = xb[j];
+                    const float ta = t0[j], tb = t1[j];
+                    y0.x = fmaf(v.x, ta, y0.x); y0.y = fmaf(v.y, ta, y0.y);
+                    y1.x = fmaf(v.x, tb, y1.x); y1.y = fmaf(v.y, tb, y1.y);
+                }
+            } else {
+                const float2 *xa = xb - 1;
+                for (int j = 0; j < T; j++) {
+                    const float2 va = xa[j], vb = xb[j];
+                    const float ta = t0[j], tb = t1[j];
+                    y0.x = fmaf(va.x, ta, y0.x); y0.y = fmaf(va.y, ta, y0.y);
+                    y1.x = fmaf(vb.x, tb, y1.x); y1.y = fmaf(vb.y, tb, y1.y);
+                }
+            }
+        } else if (P.tile_in_smem) {
             const float2 *xb = s_x + s1;
             if (!boundary) {
 #pragma unroll 4
@@ -506,7 +531,7 @@ int32_t b2s_pfbarb_exec(b2s_pfbarb *p, const void *d_in, size_t n_in, void *d_ou
     const size_t tile_items = sub_per_cta * P.sb_len + p->T + 2;
     P.tile_in_smem = tile_items * sizeof(float2) <= 64 * 1024;
     P.tile_cap = (int)tile_items;
-    const size_t arms_smem_bytes = p->num_filters * (p->T | 1) * sizeof(float2);       // odd row stride (bank conflicts)
+    const size_t arms_smem_bytes = p->num_filters * (p->T | 1) * sizeof(float);        // planar rows, odd stride
     P.arms_in_smem = arms_smem_bytes <= 64 * 1024;
     const size_t smem = 3 * kDescCap * sizeof(uint32_t) + (P.tile_in_smem ? tile_items * sizeof(float2) : 0) +
                         (P.arms_in_smem ? arms_smem_bytes : 0);
