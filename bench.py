@@ -400,6 +400,7 @@ def sec_config1_perf_fir(torch, fb, dev, args):
     # the same 30 launches captured ONCE in a CUDA graph and replayed (launch-bound inner loops belong in graphs):
     # a context on a dedicated stream, the plan created before capture, the pass captured on that stream
     graph_sec = None
+    par_sec = None
     try:
         gs = torch.cuda.Stream(dev)
         with torch.cuda.stream(gs):
@@ -412,24 +413,54 @@ def sec_config1_perf_fir(torch, fb, dev, args):
                     for s_ in range(stages):
                         c, p, st = gfir.filter(cur[:m], bufs[s_ & 1])
                         cur, m = bufs[s_ & 1], p
+
+            def replay_time(body):
+                body()
+                gs.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=gs):
+                    body()
+                for _ in range(3):
+                    g.replay()
+                gs.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(gs)
+                for _ in range(20):
+                    g.replay()
+                e1.record(gs)
+                gs.synchronize()
+                return e0.elapsed_time(e1) * 1e-3 / 20
+            graph_sec = replay_time(graph_body)
+            # the pipes are independent flowgraph branches (perf/fir/fir.rs:60-86 connects `pipes` separate chains): one
+            # stream, one context and one pair of buffers per pipe, forked from / joined to the capturing stream, so the
+            # graph holds `pipes` parallel chains of `stages` kernels
+            pstreams = [torch.cuda.Stream(dev) for _ in range(pipes)]
+            pctx = [fb.Context(dev.index, stream=ps.cuda_stream) for ps in pstreams]
+            pfir = [fb.FirFilter(taps, sample_dtype=np.float32, ctx=c) for c in pctx]
+            pbufs = [[torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(pipes)]
+            pgot = [0] * pipes
+
+            def parallel_body():
+                for i in range(pipes):
+                    pstreams[i].wait_stream(gs)
+                    cur, m = xd, n
+                    for s_ in range(stages):
+                        c, p, st = pfir[i].filter(cur[:m], pbufs[i][s_ & 1])
+                        cur, m = pbufs[i][s_ & 1], p
+                    pgot[i] = m
+                for i in range(pipes):
+                    gs.wait_stream(pstreams[i])
+            par_sec = replay_time(parallel_body)
+            assert all(m == n - stages * (ntaps - 1) for m in pgot)
+            # the parallel chains computed what the serial chain computes
             graph_body()
             gs.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=gs):
-                graph_body()
-            for _ in range(3):
-                g.replay()
-            gs.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(gs)
-            for _ in range(20):
-                g.replay()
-            e1.record(gs)
-            gs.synchronize()
-            graph_sec = e0.elapsed_time(e1) * 1e-3 / 20
+            ref_out = bufs[(stages - 1) & 1][: pgot[0]].clone()
+            for i in range(pipes):
+                assert torch.equal(pbufs[i][(stages - 1) & 1][: pgot[i]], ref_out), "parallel pipe differs from the serial chain"
     except Exception as e:  # noqa: BLE001
-        graph_sec = None
         graph_err = repr(e)[:200]
+        print(f"[bench] perf/fir graph section: {graph_err}", file=sys.stderr)
     # end to end: host vector in, host vector out per pipe (VectorSource / VectorSink roles)
     h_in = torch.from_numpy(x).pin_memory()
     h_out = torch.empty(n, dtype=torch.float32).pin_memory()
@@ -458,7 +489,11 @@ def sec_config1_perf_fir(torch, fb, dev, args):
         "cuda_graph": ({"value": pipes * n / graph_sec / 1e6, "unit": "Msamples/s", "ms_per_pass": graph_sec * 1e3,
                         "note": "the same pipes x stages launches captured once in a CUDA graph and replayed"}
                        if graph_sec else {"error": locals().get("graph_err")}),
-        "roofline": _roofline(8.0 * n * stages * pipes, min(sec, graph_sec or sec), "8 B/sample/stage; 30 launches of ~4 MB each: launch-latency bound (best of eager / graph replay); at this slice size AUTO runs the CUDA-core kernel (the tensor kernel's fixed cost is ~12 us per launch)"),
+        "cuda_graph_parallel_pipes": ({"value": pipes * n / par_sec / 1e6, "unit": "Msamples/s", "ms_per_pass": par_sec * 1e3,
+                                       "note": "one stream / context / buffer pair per pipe, forked and joined inside one CUDA graph: "
+                                               "the pipes are independent branches of the flowgraph; outputs equal the serial chain's bit for bit"}
+                                      if par_sec else {"error": locals().get("graph_err")}),
+        "roofline": _roofline(8.0 * n * stages * pipes, min(sec, graph_sec or sec, par_sec or sec), "8 B/sample/stage; 30 launches of ~4 MB each: launch-latency bound (best of eager / graph replay); at this slice size AUTO runs the CUDA-core kernel (the tensor kernel's fixed cost is ~12 us per launch)"),
         "cpu_baseline": {"value": pipes * n / cpu_s / 1e6, "unit": "Msamples/s", "cores": pipes, "kind": "port",
                          "sample": "the whole config: 5 pipes x 6 stages x 1 M samples, oracle port of fir.rs:52-91 (strict order), one thread per pipe"},
         "e2e": {"value": pipes * n / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * n * pipes,
