@@ -64,7 +64,7 @@ def test_resampler_known_answers(fb):
     assert (c, p, st) == (6, 2, 0) and list(o) == [4.0, 13.0]
 
 
-@pytest.mark.parametrize("L,M", [(3, 2), (2, 3), (1, 4), (5, 1), (48, 125), (160, 147), (7, 64)])
+@pytest.mark.parametrize("L,M", [(3, 2), (2, 3), (1, 4), (5, 1), (48, 125), (160, 147), (7, 64), (4, 3), (4, 5), (2, 1), (3, 4)])
 @pytest.mark.parametrize("cplx", [True, False])
 def test_resampler_parity(fb, rng, L, M, cplx):
     taps = orc.kaiser_multirate(L, M, 12, 1e-4)        # FirBuilder::resampling default design
