@@ -348,12 +348,13 @@ __global__ void fir_naive_kernel(const S *__restrict__ in, S *__restrict__ out,
 //      o[L*j + k0] = sum_q sum_u x_q[j + u] * G[k0][q][u],     x_q[m] = i[M*m + q]
 // with G[k0][q][u] = bank_k0[M*u + q - s_k0], s_k0 = floor(k0*M/L) (host table, zero padded to a
 // multiple of R).  A CTA stages the M phase rows of its input tile ONCE, then runs the sliding
-// register-window loop of the direct FIR L times (one pass per k0) and leaves through a shared-memory
-// transpose so that global stores are contiguous 16-byte vectors.  Compared with one thread per
-// output reading every sample from shared memory (resamp.cu) this does R*R MACs per R-item segment
-// load instead of 1.6 FMA per LDS.
+// register-window loop of the direct FIR over the L banks -- for L = 2..4 (LT = L) every window segment is
+// loaded once and multiplied into all L accumulator sets, otherwise (LT = 0) one pass per k0 -- and stages
+// each thread's R*L outputs contiguously, in final order, in shared memory (segments R*L + 1 items apart)
+// so that global stores are contiguous 16-byte vectors.  Compared with one thread per output reading every
+// sample from shared memory (resamp.cu) this does LT*R*R MACs per R-item segment load instead of 1.6 FMA
+// per LDS.
 // ---------------------------------------------------------------------------------------------
-// LT = L when it is one of the instantiated interpolation factors (all banks per segment load), else 0 (one bank at a time)
 template <typename S, int R, int THREADS, int LT>
 __global__ void __launch_bounds__(THREADS, LT == 3 ? 5 : 1)        // L = 3: 99 -> 94 registers = a fifth resident CTA, no spills
 resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *__restrict__ gtab,
@@ -449,7 +450,7 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
     } else {
         for (int k0 = 0; k0 < L; k0++) {
             S acc[R];
-    #pragma unroll
+#pragma unroll
             for (int r = 0; r < R; r++) acc[r] = zero_of<S>();
             for (int q = 0; q < M; q++)
                 fir_row<S, float, R>(acc, xs + (size_t)q * pitch * sizeof(S), q & 7, tid, gs + ((size_t)k0 * M + q) * Upad,
@@ -457,7 +458,7 @@ resamp_slide_kernel(const S *__restrict__ in, S *__restrict__ out, const float *
             // output staging in FINAL order: this thread's R*L outputs o = L*(R*tid + r) + k0 form one segment of R*L items;
             // segments are R*L + 1 items apart (odd stride: the lanes of a warp hit distinct banks)
             S *oseg = reinterpret_cast<S *>(os) + (size_t)tid * (R * L + 1) + k0;
-    #pragma unroll
+#pragma unroll
             for (int r = 0; r < R; r++) oseg[r * L] = acc[r];
         }
     }
